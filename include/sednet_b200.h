@@ -1,0 +1,244 @@
+/*
+ * sednet_b200.h -- C ABI of libsednet_b200.so: the sm_100a (B200) implementation of SED-Net's per-point
+ * inference hot path (kNN graph + EdgeConv encoder, per-point heads, mean-shift clustering, primitive fits).
+ *
+ * The reference (yuanqili78/SED-Net) has no FFI: its boundary for this path is a set of Python functions and
+ * nn.Module methods.  Every entry point below names the reference function (file:line under the reference
+ * root) it stands in for; the Python mirror of those functions (sed-net_b200/src/*.py) binds these symbols
+ * through ctypes, see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; all pointers are DEVICE pointers unless the name ends in _host;
+ *   - every function returns int: 0 = ok, SED_ERR_ARG (-1) bad argument, SED_ERR_UNSUPPORTED (-2) shape outside
+ *     the compiled range, -(1000 + cudaError_t) for CUDA failures; never throws, never exits;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises the device
+ *     unless documented ("host sync");
+ *   - tensors are dense row-major in the stated shape, f32 unless stated; indices/labels are int64 where the
+ *     reference returns torch int64.
+ */
+#ifndef SEDNET_B200_H
+#define SEDNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SED_OK 0
+#define SED_ERR_ARG (-1)
+#define SED_ERR_UNSUPPORTED (-2)
+#define SED_ERR_CUDA_BASE (-1000)
+
+typedef void* sed_stream_t; /* cudaStream_t */
+
+/* library / device info: returns the ABI version (major*100+minor). */
+int sed_version(void);
+/* human-readable text for a return code (static storage). */
+const char* sed_error_string(int code);
+
+/* ------------------------------------------------------------------ graph ops (src/PointNet.py) */
+
+/* src/PointNet.py:62-87  knn(x, k, k): x (B,C,N) -> idx (B,N,k), nearest first (self first).
+ * idx64 != 0 -> int64 output (torch convention), else int32.  C <= 128, k <= 256, k <= N. */
+int sed_knn_l2(const float* x, int B, int C, int N, int k, void* idx, int idx64, sed_stream_t stream);
+
+/* src/PointNet.py:90-137  knn_points_normals(x, k, k, W): x (B,6,N) rows 0-2 points, 3-5 normals;
+ * metric p_dist * (1 + W * (2 - 2 n.n')). */
+int sed_knn_pn(const float* x6, int B, int N, int k, float W, void* idx, int idx64, sed_stream_t stream);
+
+/* src/PointNet.py:140-171 / :174-208  get_graph_feature[_with_normals]: gathers cat([x_j - x_i, x_i]).
+ * x (B,C,N), idx (B,N,k) int64 -> out (B,2C,N,k).  (API parity only: the fused forward never materialises this.) */
+int sed_graph_feature(const float* x, const int64_t* idx, int B, int C, int N, int k, float* out,
+                      sed_stream_t stream);
+
+/* ------------------------------------------------------------------ network (src/SEDNet.py) */
+
+/* Parameter table of SEDNet with the inference driver's kwargs (generate_predictions_aug.py:142-154): device
+ * pointers to the state_dict tensors, in this order (src/SEDNet.py:31-48, :228-290). */
+enum sed_param {
+    SED_P_ENC_CONV1_W = 0, /* encoder.conv1.0.weight (64,12)   */
+    SED_P_ENC_BN1_W,       /* encoder.bn1.weight (64)          */
+    SED_P_ENC_BN1_B,
+    SED_P_ENC_CONV2_W,     /* encoder.conv2.0.weight (64,128)  */
+    SED_P_ENC_BN2_W,
+    SED_P_ENC_BN2_B,
+    SED_P_ENC_CONV3_W,     /* encoder.conv3.0.weight (128,128) */
+    SED_P_ENC_BN3_W,
+    SED_P_ENC_BN3_B,
+    SED_P_ENC_MLP1_W,      /* encoder.mlp1.weight (1024,256)   */
+    SED_P_ENC_MLP1_B,
+    SED_P_ENC_BNMLP1_W,
+    SED_P_ENC_BNMLP1_B,
+    SED_P_CONV1_W,         /* conv1.weight (512,1280)          */
+    SED_P_CONV1_B,
+    SED_P_BN1_W,
+    SED_P_BN1_B,
+    SED_P_CONV2_W,         /* conv2.weight (256,512)           */
+    SED_P_CONV2_B,
+    SED_P_BN2_W,
+    SED_P_BN2_B,
+    SED_P_PRIM1_W,         /* mlp_prim_prob1.weight (256,256)  */
+    SED_P_PRIM1_B,
+    SED_P_BN_PRIM1_W,
+    SED_P_BN_PRIM1_B,
+    SED_P_PRIM2_W,         /* mlp_prim_prob2.weight (P,256)    */
+    SED_P_PRIM2_B,
+    SED_P_EDGE0_W,         /* edge_module.0.weight (128,256)   */
+    SED_P_EDGE0_B,
+    SED_P_EDGE1_W,         /* edge_module.1 GroupNorm(4,128)   */
+    SED_P_EDGE1_B,
+    SED_P_EDGE2_W,         /* edge_module.2.weight (2,128)     */
+    SED_P_EDGE2_B,
+    SED_P_SEG1_W,          /* mlp_seg_prob1.weight (256,256)   */
+    SED_P_SEG1_B,
+    SED_P_BN_SEG1_W,
+    SED_P_BN_SEG1_B,
+    SED_P_ASIS0_W,         /* asis.0.weight (256,256)          */
+    SED_P_ASIS0_B,
+    SED_P_ASIS1_W,
+    SED_P_ASIS1_B,
+    SED_P_PRIMENC_W,       /* prim_encoding.0.weight (256,P+2) */
+    SED_P_PRIMENC_B,
+    SED_P_SEG2_W,          /* mlp_seg_prob2.weight (E,256)     */
+    SED_P_SEG2_B,
+    SED_P_COUNT
+};
+
+/* bytes of scratch sed_sednet_forward needs for (B, N, k). */
+int64_t sed_sednet_workspace_bytes(int B, int N, int k);
+
+/* src/SEDNet.py:292-342  SEDNet.forward(points, None, False) with mode=5, primitives, embedding,
+ * combine_label_prim, edge_module, late_fusion (the driver's configuration), including the encoder
+ * DGCNNEncoderGn.forward src/SEDNet.py:78-98.
+ *   params      SED_P_COUNT device pointers (host array of pointers)
+ *   points      (B,6,N)
+ *   k           nn_nb;  normal_metric_W, w_pos_enc as in the constructor;  emb_size E (<=128), num_primitives P (<=8)
+ *   embedding   (B,E,N), log_prob (B,P,N), edges (B,2,N)   outputs
+ *   x4 (B,1024), x_features (B,256,N)  optional encoder outputs (may be NULL)
+ *   workspace   sed_sednet_workspace_bytes(B,N,k) bytes */
+int sed_sednet_forward(const float* const* params_host, const float* points, int B, int N, int k,
+                       float normal_metric_W, float w_pos_enc, int emb_size, int num_primitives, float* embedding,
+                       float* log_prob, float* edges, float* x4, float* x_features, void* workspace,
+                       int64_t workspace_bytes, sed_stream_t stream);
+
+/* One EdgeConv block, src/SEDNet.py:37-45,81-92: Conv2d(2C->Cout,1x1,no bias) over cat([x_j-x_i, x_i]) ->
+ * GroupNorm(G) -> LeakyReLU(slope) -> max over k.  x (B,Cin,N) with batch stride x_bstride elements,
+ * idx (B,N,k) int32, W (Cout,2Cin), out (B,Cout,N) with batch stride out_bstride.  Cout in {64,128}.
+ * workspace: sed_edgeconv_workspace_bytes(B,N,Cout). */
+int64_t sed_edgeconv_workspace_bytes(int B, int N, int Cout);
+int sed_edgeconv_forward(const float* x, int64_t x_bstride, const int* idx, const float* W, const float* gamma,
+                         const float* beta, int B, int Cin, int Cout, int N, int k, int G, float eps, float slope,
+                         float* out, int64_t out_bstride, void* workspace, sed_stream_t stream);
+
+/* ------------------------------------------------------------------ mean-shift (src/mean_shift.py) */
+
+/* F.normalize(embedding[b].T, p=2, dim=1) (generate_predictions_aug.py:379-380): emb (B,d,N) -> X (B,N,d). */
+int sed_normalize_transpose(const float* emb, int B, int d, int N, float* X, sed_stream_t stream);
+
+/* src/mean_shift.py:115-137 compute_bandwidth on the rows given (+ the clamp(min=min_bw) of :34):
+ * X (B,N,d) unit rows, K = int(quantile*num_samples) -> bw (B).  kth_ws: B*N floats scratch. */
+int sed_ms_bandwidth(const float* X, int B, int N, int d, int K, float min_bw, float* kth_ws, float* bw,
+                     sed_stream_t stream);
+
+/* src/mean_shift.py:45-79 mean_shift_: `iterations` fixed shifts on the unit hypersphere.
+ *   X (B,N,d), bw (B) device, kernel_type 0 gaussian / 1 epanechnikov, prec_mode 0 = FP32 FFMA,
+ *   1 = tcgen05 3xTF32 (FP32-faithful split), 2 = tcgen05 single-pass TF32.
+ *   out (B,N,d); tmp (B,N,d) scratch (ping-pong). */
+int sed_ms_shift(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type,
+                 int prec_mode, float* out, float* tmp, sed_stream_t stream);
+
+/* src/mean_shift.py:139-179 nms: centers = shifted points (B,N,d), X (B,N,d), bw (B).
+ *   labels (B,N) int64; center_ids (B,max_centers) int32 ascending, n_centers (B) int32, n_labels (B) int32
+ *   (number of distinct labels in use = torch.unique(labels).shape[0]); centers_out (B,max_centers,d).
+ *   workspace: sed_ms_nms_workspace_bytes(B,N). Clouds with more than max_centers centres get n_centers = -1. */
+int64_t sed_ms_nms_workspace_bytes(int B, int N);
+int sed_ms_nms(const float* centers, const float* X, const float* bw, int B, int N, int d, int max_centers,
+               int64_t* labels, int* center_ids, int* n_centers, int* n_labels, float* centers_out,
+               void* workspace, sed_stream_t stream);
+
+/* src/segment_utils.py:536-545 to_one_hot(target, maxx): labels (N) int64 -> (N,maxx) f32. */
+int sed_one_hot(const int64_t* labels, int N, int maxx, float* out, sed_stream_t stream);
+
+/* ------------------------------------------------------------------ primitive fits (src/primitive_forward.py) */
+
+#define SED_PRIM_PLANE 1    /* src/primitive_forward.py:1006 */
+#define SED_PRIM_CONE 3     /* :1011 */
+#define SED_PRIM_CYLINDER 4 /* :1016 */
+#define SED_PRIM_SPHERE 5   /* :1021 */
+#define SED_FIT_PARAMS 8    /* floats per segment */
+
+/* Batched weighted least-squares fits, one CTA per (cloud, segment):
+ *   Fit.fit_plane_torch    src/primitive_forward.py:712-733 -> params [a0 a1 a2 d]
+ *   Fit.fit_sphere_torch   :750-773                          -> [c0 c1 c2 r]
+ *   Fit.fit_cylinder_torch :788-810                          -> [a0 a1 a2 c0 c1 c2 r]
+ *   Fit.fit_cone_torch     :812-847                          -> [c0 c1 c2 a0 a1 a2 theta]
+ *   with LeastSquares.lstsq / best_lambda src/fitting_utils.py:32-85 and the dispatch + 20-point minimum of
+ *   fit_one_shape_torch :929-1051.
+ * points, normals (B,N,3); weights (B,N) or NULL (= 1); labels (B,N) int64 or NULL (every point belongs to
+ * segment 0); seg_type (B,S) int32; params (B,S,8); status (B,S) int32: 0 fitted (full-rank), 1 skipped,
+ * 2 fitted through the regularised branch, 3 degenerate cone (cond > 1e5, :822-827). */
+int sed_fit_segments(const float* points, const float* normals, const float* weights, const int64_t* labels,
+                     const int* seg_type, int B, int N, int S, int min_pts, float* params, int* status,
+                     sed_stream_t stream);
+
+/* LeastSquares.lstsq(A, Y, lamb) src/fitting_utils.py:36-65 for one (m,3) system: x (3); status 0 full rank (QR
+ * branch), 2 regularised branch (best_lambda :68-85). */
+int sed_lstsq3(const float* A, const float* Y, int m, float* x, int* status, sed_stream_t stream);
+
+/* customsvd forward (src/fitting_utils.py:420-455, torch.svd(some=True)) of an (m,3) matrix: singular values S (3)
+ * descending and right singular vectors V (3,3) as columns (sign of each column is arbitrary, as in LAPACK). */
+int sed_svd3(const float* A, int m, float* S, float* V, sed_stream_t stream);
+
+/* ResidualLoss.residual_loss(points, parameters, sqrt) with reduce=True, src/primitives.py:36-44 over
+ * ComputePrimitiveDistance.distance_from_* :89-195: mean (guarded-sqrt) distance of each segment's points to
+ * its fitted primitive.  residual (B,S) f32 (0 for skipped segments). */
+int sed_residual_segments(const float* points, const int64_t* labels, const int* seg_type, const float* params,
+                          const int* status, int B, int N, int S, int use_sqrt, float* residual,
+                          sed_stream_t stream);
+
+/* ComputePrimitiveDistance.distance_from_{plane,sphere,cylinder,cone,torus} with reduce=False
+ * (src/primitives.py:89-111,113-127,129-161,166-195,58-87): points (n,3), params[8] device, out (n).
+ * prim: SED_PRIM_* or 7 for torus ([axis3 center3 major minor]). */
+int sed_primitive_distance(const float* points, int n, int prim, const float* params, int use_sqrt, float* out,
+                           sed_stream_t stream);
+
+/* Per-segment vote of the predicted primitive type (Fitting_patches_and_edges/residual_utils.py:245-285):
+ * log_prob (B,P,N) -> pred_type (B,N) int32 (argmax, generate_predictions_aug.py:365; with log_prob NULL the
+ * given pred_type is used as is); with labels (B,N) int64: seg_type (B,S) = mode over the segment (lowest id on
+ * ties), seg_count (B,S). */
+int sed_segment_types(const float* log_prob, const int64_t* labels, int B, int P, int N, int S, int* pred_type,
+                      int* seg_type, int* seg_count, sed_stream_t stream);
+
+/* ------------------------------------------------------------------ end-to-end step with HOST buffers */
+
+/* One inference step over a batch, generate_predictions_aug.py:213-236,365,379-387 followed by the analytic
+ * fits of every predicted segment (residual_utils.py:210-331): two forwards (type net, instance net), type
+ * argmax, normalise, guarded mean-shift (quantile *= 1.2 while > 49 labels), per-segment type vote, fits,
+ * residuals.  All *_host pointers are HOST memory (pinned for best speed); device buffers live in the handle.
+ * Synchronises `stream` before returning (host sync). */
+typedef struct sed_pipeline sed_pipeline_t;
+int sed_pipeline_create(int max_B, int N, int k, int max_segments, sed_pipeline_t** out);
+void sed_pipeline_destroy(sed_pipeline_t* p);
+/* upload the two weight sets (host arrays of HOST pointers, SED_P_COUNT each; shapes as in enum sed_param). */
+int sed_pipeline_set_weights(sed_pipeline_t* p, const float* const* type_params_host,
+                             const float* const* inst_params_host);
+/* points_host, normals_host (B,N,3); outputs: labels_host (B,N) int64, pred_type_host (B,N) int32,
+ * seg_type_host (B,S) int32, params_host (B,S,8), status_host (B,S) int32, residual_host (B,S),
+ * bw_host (B), n_labels_host (B) int32.  S = max_segments of the handle. prec_mode as in sed_ms_shift. */
+int sed_pipeline_run_host(sed_pipeline_t* p, const float* points_host, const float* normals_host, int B,
+                          float quantile, int iterations, int prec_mode, int64_t* labels_host,
+                          int* pred_type_host, int* seg_type_host, float* params_host, int* status_host,
+                          float* residual_host, float* bw_host, int* n_labels_host, sed_stream_t stream);
+/* same step with inputs already resident on the device ((B,N,3) each) and results left on the device in the
+ * handle; used for the device-resident throughput number.  sed_pipeline_device_ptr returns the named buffer. */
+int sed_pipeline_run_device(sed_pipeline_t* p, const float* points_dev, const float* normals_dev, int B,
+                            float quantile, int iterations, int prec_mode, sed_stream_t stream);
+void* sed_pipeline_device_ptr(sed_pipeline_t* p, const char* name);
+/* number of kernels the library launched since the last call with reset != 0 (for bench accounting). */
+int64_t sed_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEDNET_B200_H */
