@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""Benchmark of the SED-Net inference hot path on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--prec 0|1|2]
+
+One "step" = one pass of the hot path over one batch of 8 synthetic 10 000-point clouds per GPU (BASELINE.json
+configs[1]): two SEDNet forwards (type net, instance net), type argmax, normalise, guarded mean-shift (50
+iterations), per-segment type vote, primitive fits, residuals.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC, UNIT = "point_clouds_per_sec_10k_seg_fit", "clouds/s"
+BATCH, NPTS, KNN, ITERS, QUANTILE, DIM = 8, 10000, 64, 50, 0.015, 128
+WORKLOAD = "configs[1]: batch=8 x 10000-pt clouds, 2x SEDNet forward (k=64) + mean-shift(50 it) + type vote + fits"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_inputs(rank, batch=BATCH, n=NPTS):
+    from sednet_b200 import synth
+    pts, nrm, lab, typ = synth.make_batch(batch, n, seed0=1234 + rank * batch)
+    return pts, nrm
+
+
+def weights():
+    from sednet_b200 import synth
+    return synth.make_state_dict(0), synth.make_state_dict(1, randomize_gn=True)
+
+
+def oracle_step(pts, nrm, sd_t, sd_i):
+    """One reference-path step on the CPU (oracle port of the reference's PyTorch code) over the given clouds."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    with torch.no_grad():
+        return O.end_to_end(sd_t, sd_i, torch.from_numpy(pts), torch.from_numpy(nrm), KNN, QUANTILE, ITERS)
+
+
+def cpu_baseline_leg(budget_s=40.0):
+    """Reference path (oracle port) on the host cores over a bounded sample: 1 cloud of the batch."""
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    pts, nrm = make_inputs(0, batch=1)
+    sd_t, sd_i = weights()
+    sd_t = {k: torch.from_numpy(v) for k, v in sd_t.items()}
+    sd_i = {k: torch.from_numpy(v) for k, v in sd_i.items()}
+    t0 = time.perf_counter()
+    oracle_step(pts, nrm, sd_t, sd_i)
+    dt = time.perf_counter() - t0
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"1 of the {BATCH} clouds of one step (10000 pts, full path, oracle/oracle.py end_to_end), {dt:.1f} s"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation (the oracle port: the reference is Python and does not
+    travel to the GPU box) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    sd_t, sd_i = weights()
+    sd_t = {k: torch.from_numpy(v) for k, v in sd_t.items()}
+    sd_i = {k: torch.from_numpy(v) for k, v in sd_i.items()}
+    pts, nrm = make_inputs(0, batch=1)
+    budget = float(os.environ.get("SEDNET_REF_BUDGET_S", "150"))
+    t_start = time.perf_counter()
+    warm = 0
+    if args.warmup > 0:  # one bounded warm-up step (threads, allocator)
+        oracle_step(pts[:, :2048].copy(), nrm[:, :2048].copy(), sd_t, sd_i)
+        warm = 1
+    times = []
+    for _ in range(max(1, args.steps)):
+        t0 = time.perf_counter()
+        oracle_step(pts, nrm, sd_t, sd_i)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start + times[-1] > budget:
+            break
+    dt = float(np.mean(times))
+    v = 1.0 / dt
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times), "warmup": warm,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "sample": "each step = 1 cloud (10000 pts) of the batch, full path"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": f"{len(times)} step(s) of 1 cloud x 10000 pts (oracle/oracle.py end_to_end); "
+                                       f"requested steps {args.steps}, time budget {budget:.0f} s"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from sednet_b200.pipeline import Pipeline, launches
+    from sednet_b200.src import _lib
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.load()
+    pts, nrm = make_inputs(rank)
+    sd_t, sd_i = weights()
+    pipe = Pipeline(BATCH, NPTS, KNN, max_segments=64)
+    pipe.set_weights(sd_t, sd_i)
+    P_host, N_host = torch.from_numpy(pts).pin_memory(), torch.from_numpy(nrm).pin_memory()
+    P_dev, N_dev = P_host.to(dev), N_host.to(dev)
+    rec = torch.zeros((BATCH, 4), dtype=torch.float32, device=dev)
+    gathered = torch.zeros((world * BATCH, 4), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def gather_records():
+        # per-shape records (n_labels, n_fitted, mean residual, bw) all-gathered across ranks: the only collective
+        if world > 1:
+            st = (pipe.device_tensor_view("status") != 1).sum(1).float()
+            rec[:, 0] = pipe.device_tensor_view("n_labels").float()
+            rec[:, 1] = st
+            rec[:, 2] = pipe.device_tensor_view("residual").sum(1) / st.clamp(min=1)
+            rec[:, 3] = pipe.device_tensor_view("bw")
+            dist.all_gather_into_tensor(gathered, rec)
+
+    def step_device():
+        pipe.run_device(P_dev, N_dev, QUANTILE, ITERS, args.prec)
+        gather_records()
+
+    def step_host():
+        out = pipe.run_host(P_host, N_host, QUANTILE, ITERS, args.prec)
+        gather_records()
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches(reset=True)
+    ms_dev = timed(step_device, args.steps)
+    n_launch = launches()
+    stage, retries = pipe.stage_ms()
+    clocks = sampler.stop() if rank == 0 else None
+    step_host()
+    ms_host = timed(step_host, args.steps)
+    out = step_host()
+
+    value = world * BATCH * args.steps / (ms_dev / 1e3)
+    e2e = world * BATCH * args.steps / (ms_host / 1e3)
+    h2d = 2 * BATCH * NPTS * 3 * 4
+    d2h = sum(int(v.numel() * v.element_size()) for v in out.values())
+    hbm_peak, tf_peak, how = peaks()
+    # dominant kernel: the mean-shift iteration (one launch per iteration per batch).  Algorithmic FLOP per launch:
+    # 2 GEMMs x 2*N*N*d per cloud; duration from the CUDA events the library records around the
+    # shift stage on the run's stream.
+    flop_per_launch = BATCH * 2 * 2.0 * NPTS * NPTS * DIM
+    t_launch = stage["shift"] / 1e3 / ITERS
+    achieved = flop_per_launch / t_launch / 1e12
+    roof = {"kernel": {0: "ms_shift_ffma_kernel", 1: "ms_shift_tc_kernel(3xTF32)", 2: "ms_shift_tc_kernel(TF32)"}[args.prec],
+            "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+            "traffic": None, "peak_source": how + " dense bf16 sustained; the kernel computes in "
+            + ("FP32 FFMA (CUDA cores)" if args.prec == 0 else "TF32 on tcgen05 (half the bf16 rate)"),
+            "share_of_step": stage["shift"] / (ms_dev / args.steps)}
+    if rank == 0:
+        cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu else None
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.prec == 0 else "tf32x3" if args.prec == 1 else "tf32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "clouds_per_gpu": BATCH, "points": NPTS, "k": KNN,
+                           "ms_iterations": ITERS, "ms_prec_mode": args.prec, "parallelism": f"dp{world}",
+                           "l2": "no explicit flush: each step streams ~1 GB of activations/workspace per GPU (> 126 MB L2)",
+                           "guard_retries": retries},
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "ms_per_step": ms_host / args.steps},
+                "gpu_launches": n_launch, "clocks": clocks, "roofline": roof,
+                "stage_ms": stage}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--prec", type=int, default=int(os.environ.get("SEDNET_B200_MS_PREC", "0")))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -227,14 +227,18 @@ int sed_pipeline_set_weights(sed_pipeline_t* p, const float* const* type_params_
  * seg_type_host (B,S) int32, params_host (B,S,8), status_host (B,S) int32, residual_host (B,S),
  * bw_host (B), n_labels_host (B) int32.  S = max_segments of the handle. prec_mode as in sed_ms_shift. */
 int sed_pipeline_run_host(sed_pipeline_t* p, const float* points_host, const float* normals_host, int B,
-                          float quantile, int iterations, int prec_mode, int64_t* labels_host,
+                          double quantile, int iterations, int prec_mode, int64_t* labels_host,
                           int* pred_type_host, int* seg_type_host, float* params_host, int* status_host,
                           float* residual_host, float* bw_host, int* n_labels_host, sed_stream_t stream);
 /* same step with inputs already resident on the device ((B,N,3) each) and results left on the device in the
  * handle; used for the device-resident throughput number.  sed_pipeline_device_ptr returns the named buffer. */
 int sed_pipeline_run_device(sed_pipeline_t* p, const float* points_dev, const float* normals_dev, int B,
-                            float quantile, int iterations, int prec_mode, sed_stream_t stream);
+                            double quantile, int iterations, int prec_mode, sed_stream_t stream);
 void* sed_pipeline_device_ptr(sed_pipeline_t* p, const char* name);
+/* device time (ms, CUDA events on the run's stream) of the stages of the last run: forward(type net),
+ * forward(instance net)+normalise, bandwidth, shift iterations, nms (+ guard retries), type vote + fits +
+ * residuals; retries = number of guard re-runs. Waits for the run to finish. */
+int sed_pipeline_stage_ms(sed_pipeline_t* p, float* ms6_host, int* retries_host);
 /* number of kernels the library launched since the last call with reset != 0 (for bench accounting). */
 int64_t sed_launch_count(int reset);
 

@@ -72,6 +72,9 @@ struct sed_pipeline {
     int64_t fwd_ws_bytes;
     // pinned host scratch
     int* h_counts;  // [2*max_B]: n_labels, n_centers
+    // stage boundaries of the last run: start, fwd(type), fwd(inst)+normalise, bandwidth, shift, nms, fits
+    cudaEvent_t ev[7];
+    int retries;
 };
 
 static int pipe_alloc(void** p, size_t bytes) {
@@ -105,6 +108,8 @@ void sed_pipeline_destroy(sed_pipeline_t* p) {
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (p->h_counts) cudaFreeHost(p->h_counts);
+    for (auto& e : p->ev)
+        if (e) cudaEventDestroy(e);
     delete p;
 }
 
@@ -131,6 +136,8 @@ int sed_pipeline_create(int max_B, int N, int k, int max_segments, sed_pipeline_
     PALLOC(fwd_ws, p->fwd_ws_bytes); PALLOC(nms_ws, sed_ms_nms_workspace_bytes(max_B, N));
 #undef PALLOC
     if (rc == SED_OK && cudaMallocHost((void**)&p->h_counts, 2 * B * sizeof(int)) != cudaSuccess) rc = SED_ERR_CUDA_BASE - 2;
+    for (auto& e : p->ev)
+        if (rc == SED_OK && cudaEventCreate(&e) != cudaSuccess) rc = SED_ERR_CUDA_BASE - 2;
     if (rc != SED_OK) { sed_pipeline_destroy(p); return rc; }
     *out = p;
     return SED_OK;
@@ -155,34 +162,42 @@ int sed_pipeline_set_weights(sed_pipeline_t* p, const float* const* type_params_
 }
 
 // mean-shift of clouds [b0, b0+nb) with K = int(quantile * 10000) (generate_predictions_aug.py:25-35, src/mean_shift.py:19-43)
-static int pipe_mean_shift(sed_pipeline* p, int b0, int nb, double quantile, int iterations, int prec_mode, cudaStream_t st) {
+static int pipe_mean_shift(sed_pipeline* p, int b0, int nb, double quantile, int iterations, int prec_mode, bool mark,
+                           cudaStream_t st) {
     const int64_t N = p->N, d = p->d, S = p->S;
     const int K = (int)(quantile * 10000.0);
     const float* X = p->X + b0 * N * d;
     SED_TRY(sed_ms_bandwidth(X, nb, (int)N, (int)d, K, 0.003f, p->kth + b0 * N, p->bw + b0, st));
+    if (mark) SED_CUDA(cudaEventRecord(p->ev[3], st));
     SED_TRY(sed_ms_shift(X, p->bw + b0, nb, (int)N, (int)d, iterations, 0, prec_mode, p->shifted + b0 * N * d,
                          p->tmp + b0 * N * d, st));
+    if (mark) SED_CUDA(cudaEventRecord(p->ev[4], st));
     SED_TRY(sed_ms_nms(p->shifted + b0 * N * d, X, p->bw + b0, nb, (int)N, (int)d, (int)S, (int64_t*)p->labels + b0 * N,
                        p->center_ids + b0 * S, p->n_centers + b0, p->n_labels + b0, p->centers + b0 * S * d, p->nms_ws, st));
+    if (mark) SED_CUDA(cudaEventRecord(p->ev[5], st));
     return SED_OK;
 }
 
-int sed_pipeline_run_device(sed_pipeline_t* p, const float* points_dev, const float* normals_dev, int B, float quantile,
+int sed_pipeline_run_device(sed_pipeline_t* p, const float* points_dev, const float* normals_dev, int B, double quantile,
                             int iterations, int prec_mode, sed_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!p || !points_dev || !normals_dev || B <= 0 || B > p->max_B || !p->have_weights) return SED_ERR_ARG;
     const int N = p->N, S = p->S;
+    p->retries = 0;
+    SED_CUDA(cudaEventRecord(p->ev[0], st));
     pack_input_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(points_dev, normals_dev, N, p->inp);
     SED_CHECK_LAUNCH();
     // type network, then instance network (generate_predictions_aug.py:224-229); only the outputs the driver keeps
     SED_TRY(sed_sednet_forward(p->wptr[0], p->inp, B, N, p->k, 1.0f, 0.2f, p->E, p->NP, p->emb, p->logp, p->edges, nullptr,
                                nullptr, p->fwd_ws, p->fwd_ws_bytes, st));
     SED_TRY(sed_segment_types(p->logp, nullptr, B, p->NP, N, S, p->pred_type, nullptr, nullptr, st));
+    SED_CUDA(cudaEventRecord(p->ev[1], st));
     SED_TRY(sed_sednet_forward(p->wptr[1], p->inp, B, N, p->k, 1.0f, 0.2f, p->E, p->NP, p->emb, p->logp, p->edges, nullptr,
                                nullptr, p->fwd_ws, p->fwd_ws_bytes, st));
     SED_TRY(sed_normalize_transpose(p->emb, B, p->E, N, p->X, st));
+    SED_CUDA(cudaEventRecord(p->ev[2], st));
     // guarded mean-shift: re-run a cloud with quantile * 1.2 while it has more than 49 labels
-    SED_TRY(pipe_mean_shift(p, 0, B, (double)quantile, iterations, prec_mode, st));
+    SED_TRY(pipe_mean_shift(p, 0, B, (double)quantile, iterations, prec_mode, true, st));
     SED_CUDA(cudaMemcpyAsync(p->h_counts, p->n_labels, B * sizeof(int), cudaMemcpyDeviceToHost, st));
     SED_CUDA(cudaMemcpyAsync(p->h_counts + p->max_B, p->n_centers, B * sizeof(int), cudaMemcpyDeviceToHost, st));
     SED_CUDA(cudaStreamSynchronize(st));
@@ -193,7 +208,8 @@ int sed_pipeline_run_device(sed_pipeline_t* p, const float* points_dev, const fl
             q *= 1.2;
             ++tries;
             if ((int)(q * 10000.0) > N) break;  // the reference's topk would raise here
-            SED_TRY(pipe_mean_shift(p, b, 1, q, iterations, prec_mode, st));
+            ++p->retries;
+            SED_TRY(pipe_mean_shift(p, b, 1, q, iterations, prec_mode, false, st));
             SED_CUDA(cudaMemcpyAsync(p->h_counts + b, p->n_labels + b, sizeof(int), cudaMemcpyDeviceToHost, st));
             SED_CUDA(cudaMemcpyAsync(p->h_counts + p->max_B + b, p->n_centers + b, sizeof(int), cudaMemcpyDeviceToHost, st));
             SED_CUDA(cudaStreamSynchronize(st));
@@ -206,10 +222,19 @@ int sed_pipeline_run_device(sed_pipeline_t* p, const float* points_dev, const fl
                              p->seg_type, B, N, S, 20, p->params, p->status, st));
     SED_TRY(sed_residual_segments(points_dev, (const int64_t*)p->labels, p->seg_type, p->params, p->status, B, N, S, 1,
                                   p->residual, st));
+    SED_CUDA(cudaEventRecord(p->ev[6], st));
     return SED_OK;
 }
 
-int sed_pipeline_run_host(sed_pipeline_t* p, const float* points_host, const float* normals_host, int B, float quantile,
+int sed_pipeline_stage_ms(sed_pipeline_t* p, float* ms6_host, int* retries_host) {
+    if (!p || !ms6_host) return SED_ERR_ARG;
+    SED_CUDA(cudaEventSynchronize(p->ev[6]));
+    for (int i = 0; i < 6; ++i) SED_CUDA(cudaEventElapsedTime(&ms6_host[i], p->ev[i], p->ev[i + 1]));
+    if (retries_host) *retries_host = p->retries;
+    return SED_OK;
+}
+
+int sed_pipeline_run_host(sed_pipeline_t* p, const float* points_host, const float* normals_host, int B, double quantile,
                           int iterations, int prec_mode, int64_t* labels_host, int* pred_type_host, int* seg_type_host,
                           float* params_host, int* status_host, float* residual_host, float* bw_host, int* n_labels_host,
                           sed_stream_t stream) {

@@ -79,28 +79,38 @@ class Pipeline:
         _lib.call("sed_pipeline_run_device", self._h, _lib.ptr(points), _lib.ptr(normals), B, float(quantile),
                   int(iterations), int(prec_mode), _lib.stream())
 
+    STAGES = ("forward_type", "forward_inst", "bandwidth", "shift", "nms", "fit")
+
+    def stage_ms(self):
+        """Device time of each stage of the last run (CUDA events on the run's stream) and the guard retries."""
+        ms, r = (C.c_float * 6)(), C.c_int()
+        _lib.call("sed_pipeline_stage_ms", self._h, ms, C.byref(r))
+        return dict(zip(self.STAGES, [float(v) for v in ms])), int(r.value)
+
     _SHAPES = dict(labels=("BN", torch.int64), pred_type=("BN", torch.int32), seg_type=("BS", torch.int32),
                    params=("BS8", torch.float32), status=("BS", torch.int32), residual=("BS", torch.float32),
                    bw=("B", torch.float32), n_labels=("B", torch.int32), n_centers=("B", torch.int32),
                    X=("BNd", torch.float32), shifted=("BNd", torch.float32), embedding=("BdN", torch.float32),
                    log_prob=("B6N", torch.float32))
 
-    def device_tensor(self, name):
-        """Copy of a named device buffer of the handle as a torch CUDA tensor (debug / parity checks)."""
+    def device_tensor_view(self, name):
+        """Zero-copy torch view of a named device buffer of the handle (valid for the handle's lifetime)."""
         code, dt = self._SHAPES[name]
         dims = dict(B=self.B, N=self.N, S=self.S, d=128)
         shape = tuple(dims[c] if c in dims else int(c) for c in code)
         p = _lib.load().sed_pipeline_device_ptr(self._h, name.encode())
         if not p:
             raise KeyError(name)
-        n = int(np.prod(shape))
-        out = torch.empty(shape, dtype=dt, device="cuda")
+        typestr = {torch.float32: "<f4", torch.int32: "<i4", torch.int64: "<i8"}[dt]
+
+        class _Buf:
+            __cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(p), False), "version": 2}
+        return torch.as_tensor(_Buf(), device=torch.device("cuda", torch.cuda.current_device()))
+
+    def device_tensor(self, name):
+        """Copy of a named device buffer (debug / parity checks)."""
         torch.cuda.synchronize()
-        rt = C.CDLL("libcudart.so.12")
-        rc = rt.cudaMemcpy(C.c_void_p(out.data_ptr()), C.c_void_p(p), C.c_size_t(n * out.element_size()), 3)
-        if rc != 0:
-            raise RuntimeError(f"cudaMemcpy failed: {rc}")
-        return out
+        return self.device_tensor_view(name).clone()
 
 
 def launches(reset=False):

@@ -42,9 +42,10 @@ SIGNATURES = {
     "sed_pipeline_create": (I, [I, I, I, I, C.POINTER(C.c_void_p)]),
     "sed_pipeline_destroy": (None, [c_vp]),
     "sed_pipeline_set_weights": (I, [c_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
-    "sed_pipeline_run_host": (I, [c_vp, c_vp, c_vp, I, F, I, I, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "sed_pipeline_run_device": (I, [c_vp, c_f32p, c_f32p, I, F, I, I, c_vp]),
+    "sed_pipeline_run_host": (I, [c_vp, c_vp, c_vp, I, D, I, I, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sed_pipeline_run_device": (I, [c_vp, c_f32p, c_f32p, I, D, I, I, c_vp]),
     "sed_pipeline_device_ptr": (c_vp, [c_vp, C.c_char_p]),
+    "sed_pipeline_stage_ms": (I, [c_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "sed_launch_count": (L, [I]),
 }
 

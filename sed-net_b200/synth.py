@@ -123,7 +123,8 @@ def make_cloud(seed, n_points=10000, n_patches=None, normal_jitter=0.0, min_pts=
     P = P - P.mean(0, keepdims=True)
     P = P / (np.max(P.max(0) - P.min(0)) + EPS)
     P, Nn = _pca_align(P, Nn)
-    return (P.astype(np.float32), Nn.astype(np.float32), L.astype(np.int64), T.astype(np.int64), patches)
+    return (np.ascontiguousarray(P, dtype=np.float32), np.ascontiguousarray(Nn, dtype=np.float32),
+            L.astype(np.int64), T.astype(np.int64), patches)
 
 
 def make_batch(batch, n_points=10000, seed0=1234, **kw):

@@ -38,3 +38,34 @@ def sign_align(a, ref):
 def rel_err(a, ref):
     a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
     return float(np.max(np.abs(a - ref)) / max(np.max(np.abs(ref)), 1e-12))
+
+
+def cylinder_fp64(p, n, w, eps32=float(np.finfo(np.float32).eps)):
+    """FP64 evaluation of the reference's cylinder fit formulas (src/primitive_forward.py:788-810 + :750-773 +
+    src/fitting_utils.py:36-85) with the FP32 rank tolerances of torch.matrix_rank: what the formulas give without
+    the rounding noise of the FP32 explicit-inverse solve (cond ~ 1e6 in the regularised branch).  Returns
+    axis (3,), centre (3,), radius."""
+    p, n, w = (np.asarray(v, np.float64) for v in (p, n, w))
+    w = w.reshape(-1, 1)
+    _, V = np.linalg.eigh((w * n).T @ (w * n))
+    ax = V[:, 0] / (np.linalg.norm(V[:, 0]) + eps32)
+    v = p - (p @ ax)[:, None] * ax
+    ws = w.sum() + eps32
+    m = (w * v).sum(0) / ws
+    q = (v * v).sum(1)
+    tq = (w[:, 0] * q).sum() / ws
+    A = 2 * w * (m - v)
+    Y = w[:, 0] * (w[:, 0] * q - tq)
+    AtA = A.T @ A
+    mu = np.linalg.eigvalsh(AtA)
+    smax, smin = np.sqrt(max(mu[2], 0)), np.sqrt(max(mu[0], 0))
+    lam = 0.0
+    if not smin > smax * max(A.shape[0], 3) * eps32:
+        lam = 1e-6
+        for _ in range(7):
+            if (mu[0] + lam) > (mu[2] + lam) * 3 * eps32:
+                break
+            lam *= 10
+    c = -np.linalg.solve(AtA + lam * np.eye(3), A.T @ Y)
+    r2 = (w[:, 0] * ((v - c) ** 2).sum(1)).sum() / ws
+    return ax, c, float(np.sqrt(max(r2, 1e-3)))

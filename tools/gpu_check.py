@@ -141,6 +141,18 @@ def stage_pipeline():
     with torch.no_grad():
         ref = O.end_to_end({kk: t(v) for kk, v in sd_t.items()}, {kk: t(v) for kk, v in sd_i.items()}, t(pts), t(nrm), k)
     print(f"oracle end_to_end {time.perf_counter() - t0:.1f} s")
+    Xg = pipe.device_tensor("X").cpu()
+    embg = pipe.device_tensor("embedding").cpu()
+    with torch.no_grad():
+        inp = torch.cat([t(pts), t(nrm)], 2).permute(0, 2, 1).contiguous()
+        emb_o = O.sednet_forward({kk: t(v) for kk, v in sd_i.items()}, inp, k)[0]
+    print("  embedding diff", float((embg[:B] - emb_o).abs().max()), "emb abs max", float(emb_o.abs().max()))
+    for b in range(B):
+        Xo = torch.nn.functional.normalize(emb_o[b].T, p=2, dim=1)
+        print(f"  X diff {float((Xg[b] - Xo).abs().max()):.3e} bw oracle(Xo) {float(O.ms_bandwidth(Xo, 10000, 0.015)):.6f} "
+              f"bw oracle(Xgpu) {float(O.ms_bandwidth(Xg[b], 10000, 0.015)):.6f}")
+        ms = mean_shift.MeanShift()
+        print(f"  bw gpu(Xo) {float(ms.compute_bandwidth(Xo.to(dev), 10000, 0.015)):.6f} gpu(Xgpu) {float(ms.compute_bandwidth(Xg[b].to(dev), 10000, 0.015)):.6f}")
     for b in range(B):
         r = ref[b]
         same = (canon(out["labels"][b].numpy()) == canon(r["labels"])).all()
