@@ -202,6 +202,16 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize()
+    if os.environ.get("SEDNET_BENCH_VERBOSE"):
+        for i in range(3):
+            t0 = time.perf_counter()
+            step_device()
+            t1 = time.perf_counter()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            st, _ = pipe.stage_ms()
+            print(f"[verbose] step {i}: host enqueue {1e3 * (t1 - t0):.1f} ms, total {1e3 * (t2 - t0):.1f} ms, "
+                  f"stage sum {sum(st.values()):.1f} ms {st}", file=sys.stderr)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
