@@ -35,6 +35,20 @@ int head_combine(const float* ys, const float* as_, const float* ss, const float
                  const float* sa, const float* pe, float w, int B, int C, int N, float* out, cudaStream_t st);
 int log_softmax(const float* x, long long x_bstride, int B, int C, int N, float* out, cudaStream_t st);
 
+// Stream-ordered scratch comes from the device's default memory pool; keep freed blocks cached across synchronisation
+// points (the default release threshold of 0 hands them back to the driver at every sync).
+inline void ensure_pool_config() {
+    static bool done = false;
+    if (done) return;
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done = true;
+}
+
 inline int64_t align_up(int64_t v, int64_t a = 256) { return (v + a - 1) / a * a; }
 
 // bump allocator over a caller-provided workspace

@@ -6,6 +6,9 @@
 // streams candidate tiles of 128 points through shared memory, evaluates the metric with
 // register-tiled FP32 FFMA in the reference's operation order, and keeps the running top-k of
 // each row in shared memory (threshold filter + lazy bitonic merge).
+#include <stdlib.h>
+#include <string.h>
+
 #include "internal.h"
 
 namespace sed {
@@ -404,8 +407,28 @@ __global__ void bandwidth_mean_kernel(const float* __restrict__ kth, int N, floa
 
 namespace sed {
 
+// tensor-core implementations (select_tc.cu); SED_ERR_UNSUPPORTED when the shape is outside their range
+int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn, float W, void* idx, int idx64,
+           cudaStream_t st);
+int cos_select_tc(const float* Q, const float* Cand, int B, int Nq, int Nc, const int* nc_ptr, int d, int K,
+                  float* kth_out, void* idx_out, int idx64, cudaStream_t st);
+
+// SEDNET_B200_SELECT=ffma forces the CUDA-core kernels of this file (A/B comparisons); default: tensor cores
+static bool use_tc() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SEDNET_B200_SELECT");
+        v = (e && !strcmp(e, "ffma")) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 int knn_l2(const float* x, long long bstride, int B, int C, int N, int k, void* idx, int idx64, cudaStream_t st) {
     if (!x || !idx || B <= 0 || C <= 0 || C > 128 || N < k || k <= 0) return SED_ERR_ARG;
+    if (use_tc()) {
+        const int rc = knn_tc(x, bstride, B, C, N, k, 0, 0.f, idx, idx64, st);
+        if (rc != SED_ERR_UNSUPPORTED) return rc;
+    }
     KnnParams p{};
     p.xq = p.xc = x; p.q_bstride = p.c_bstride = bstride; p.ldq = p.ldc = N;
     p.C = C; p.Nq = p.Nc = N; p.k = k; p.W = 0.f; p.out_idx = idx; p.idx64 = idx64;
@@ -414,6 +437,10 @@ int knn_l2(const float* x, long long bstride, int B, int C, int N, int k, void* 
 
 int knn_pn(const float* x6, long long bstride, int B, int N, int k, float W, void* idx, int idx64, cudaStream_t st) {
     if (!x6 || !idx || B <= 0 || N < k || k <= 0) return SED_ERR_ARG;
+    if (use_tc()) {
+        const int rc = knn_tc(x6, bstride, B, 6, N, k, 1, W, idx, idx64, st);
+        if (rc != SED_ERR_UNSUPPORTED) return rc;
+    }
     KnnParams p{};
     p.xq = p.xc = x6; p.q_bstride = p.c_bstride = bstride; p.ldq = p.ldc = N;
     p.C = 6; p.Nq = p.Nc = N; p.k = k; p.W = W; p.out_idx = idx; p.idx64 = idx64;
@@ -425,6 +452,10 @@ int knn_pn(const float* x6, long long bstride, int B, int N, int k, float W, voi
 int nearest_cos(const float* Q, const float* Cand, int B, int Nq, int Nc, const int* nc_ptr, int d, void* out,
                 int idx64, cudaStream_t st) {
     if (!Q || !Cand || !out || B <= 0 || d <= 0 || d > 128 || (d & 3) || Nq <= 0 || Nc <= 0) return SED_ERR_ARG;
+    if (use_tc()) {
+        const int rc = cos_select_tc(Q, Cand, B, Nq, Nc, nc_ptr, d, 1, nullptr, out, idx64, st);
+        if (rc != SED_ERR_UNSUPPORTED) return rc;
+    }
     KnnParams p{};
     p.xq = Q; p.xc = Cand; p.q_bstride = (long long)Nq * d; p.c_bstride = (long long)Nc * d; p.ldq = p.ldc = d;
     p.C = d; p.Nq = Nq; p.Nc = Nc; p.k = 1; p.out_idx = out; p.idx64 = idx64; p.nc_ptr = nc_ptr;
@@ -452,7 +483,13 @@ int sed_ms_bandwidth(const float* X, int B, int N, int d, int K, float min_bw, f
     KnnParams p{};
     p.xq = p.xc = X; p.q_bstride = p.c_bstride = (long long)N * d; p.ldq = p.ldc = d;
     p.C = d; p.Nq = p.Nc = N; p.k = K; p.W = 0.f; p.out_idx = nullptr; p.idx64 = 0; p.out_kth = kth_ws;
-    int rc;
+    int rc = use_tc() ? cos_select_tc(X, X, B, N, N, nullptr, d, K, kth_ws, nullptr, 0, st) : SED_ERR_UNSUPPORTED;
+    if (rc == SED_OK) {
+        bandwidth_mean_kernel<<<B, 1024, 0, st>>>(kth_ws, N, bw, min_bw);
+        SED_CHECK_LAUNCH();
+        return SED_OK;
+    }
+    if (rc != SED_ERR_UNSUPPORTED) return rc;
     if (K <= 64) rc = launch_knn<M_COS, L_ROW_MAJOR, uint32_t, 64, 64, 256, false>(p, B, st);
     else if (K <= 256) rc = launch_knn<M_COS, L_ROW_MAJOR, uint32_t, 64, 256, 512, false>(p, B, st);
     else if (K <= 512) rc = launch_knn<M_COS, L_ROW_MAJOR, uint32_t, 32, 512, 1024, false>(p, B, st);

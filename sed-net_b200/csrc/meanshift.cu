@@ -389,6 +389,7 @@ int sed_ms_shift(const float* X, const float* bw, int B, int N, int d, int itera
     if (prec_mode != 0) return SED_ERR_ARG;
     // XT lives in the second half of tmp's allocation?  No: tmp is exactly (B,N,d); the channel-major copy of X is
     // allocated from the stream-ordered pool (freed after the last iteration is enqueued).
+    ensure_pool_config();
     float* XT = nullptr;
     SED_CUDA(cudaMallocAsync((void**)&XT, (size_t)B * N * d * sizeof(float), st));
     dim3 tg((N + 31) / 32, (d + 31) / 32, B);

@@ -17,10 +17,7 @@
 //     prec_mode 2:  S = Qh Xh,                               O = Ph Xh           (fast)
 // The scale 8 keeps hi/lo away from the bottom of the FP16 range; 64 = 8*8 is folded into the exp2 argument and
 // the factor 8 on O vanishes in the normalisation.
-#include <cuda.h>
-#include <cuda_fp16.h>
-
-#include "internal.h"
+#include "tc_common.cuh"
 
 namespace sed {
 
@@ -28,106 +25,8 @@ constexpr int TC_M = 128;        // query rows per CTA  (UMMA M)
 constexpr int TC_NK = 128;       // keys per tile        (UMMA N of S, K of PV)
 constexpr int TC_D = 128;        // channels             (K of S, N of PV)
 constexpr int TC_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 exp/epilogue
-constexpr int BOX_BYTES = 128 * 128;            // one TMA box: 128 rows x 64 fp16 (128 B, one swizzle atom wide)
 constexpr int TILE_BYTES = 2 * BOX_BYTES;       // 128 rows x 128 fp16
 constexpr float kOperandScale = 8.0f;
-
-// ---------------------------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// D[tmem] (+)= A[smem] . B[smem]
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-// D[tmem] (+)= A[tmem] . B[smem]
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-        : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// Shared-memory matrix descriptor (tcgen05): 128B swizzle, SBO = 1024 B (8 rows x 128 B), version 1.
-//   K-major  operand: LBO field unused by the swizzled layouts (set to 1);
-//   MN-major operand: LBO = byte distance between the two 64-element halves of the MN extent.
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address  bits [0,14)
-    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // leading byte offset bits [16,30)
-    d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;        // stride byte offset bits [32,46)
-    d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-    return d;
-}
-// Instruction descriptor kind::f16: D = F32, A = B = F16, M = 128, N = 128; b_mn_major selects the B layout.
-__host__ __device__ constexpr uint32_t make_idesc(int b_mn_major) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | ((uint32_t)b_mn_major << 16) | ((128u >> 3) << 17) |
-           ((128u >> 4) << 24);
-}
 
 struct TcParams {
     const float* bw;        // (B)
@@ -375,37 +274,6 @@ __global__ void split_f16_kernel(const float* __restrict__ x, long long n, __hal
     if (lo) *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<const uint2*>(l);
 }
 
-// ---------------------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void* ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)ptr;
-    }
-    return fn;
-}
-
-// (B, N, 128) fp16 row-major, box 128 rows x 64 channels, 128B swizzle, out-of-range rows read as zero
-static int make_map(CUtensorMap* m, const __half* base, int B, int N) {
-    EncodeTiledFn fn = get_encode_fn();
-    if (!fn) return SED_ERR_UNSUPPORTED;
-    const cuuint64_t dims[3] = {(cuuint64_t)TC_D, (cuuint64_t)N, (cuuint64_t)B};
-    const cuuint64_t strides[2] = {(cuuint64_t)TC_D * 2, (cuuint64_t)N * TC_D * 2};
-    const cuuint32_t box[3] = {64, 128, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return r == CUDA_SUCCESS ? SED_OK : SED_ERR_CUDA_BASE - 1;
-}
-
 template <int NS, int NV>
 static int launch_tc(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& xh, const CUtensorMap& xl,
                      const TcParams& p, int B, cudaStream_t st) {
@@ -427,6 +295,7 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
     const bool has_lo = (prec_mode == 1);
     const size_t elems = (size_t)B * N * TC_D;
     // fp16 operands: X (hi, lo) and two ping-pong Q buffers (hi, lo)
+    ensure_pool_config();
     __half* buf = nullptr;
     SED_CUDA(cudaMallocAsync((void**)&buf, elems * sizeof(__half) * 6, st));
     __half *xh = buf, *xl = buf + elems, *qh[2] = {buf + 2 * elems, buf + 4 * elems},
@@ -434,11 +303,11 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
     split_f16_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, st>>>(X, (long long)elems, xh, xl);
     ++g_sed_launches;
     CUtensorMap mxh, mxl, mqh[2], mql[2];
-    int rc = make_map(&mxh, xh, B, N);
-    if (rc == SED_OK) rc = make_map(&mxl, xl, B, N);
+    int rc = make_map_f16(&mxh, xh, B, N, TC_D);
+    if (rc == SED_OK) rc = make_map_f16(&mxl, xl, B, N, TC_D);
     for (int i = 0; i < 2 && rc == SED_OK; ++i) {
-        rc = make_map(&mqh[i], qh[i], B, N);
-        if (rc == SED_OK) rc = make_map(&mql[i], ql[i], B, N);
+        rc = make_map_f16(&mqh[i], qh[i], B, N, TC_D);
+        if (rc == SED_OK) rc = make_map_f16(&mql[i], ql[i], B, N, TC_D);
     }
     for (int it = 0; it < iterations && rc == SED_OK; ++it) {
         // iteration 0 reads Q = X; iteration it > 0 reads ping-pong buffer (it-1)&1 and writes buffer it&1

@@ -1,0 +1,554 @@
+// Fused pairwise-score + exact top-k selection on the tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Serves   knn                 src/PointNet.py:62-87    (negative squared L2 in Gram form, k nearest, sorted)
+//          knn_points_normals  src/PointNet.py:90-137   (point x normal metric of the first EdgeConv layer)
+//          compute_bandwidth   src/mean_shift.py:130-135 (K-th smallest cosine distance of every row)
+//          nms membership/labels src/mean_shift.py:146-149,177-178 (nearest centre of every point)
+//
+// The N x N score matrix is never written anywhere: a CTA owns 128 query rows, the 128-candidate tiles stream through
+// shared memory by TMA, tcgen05.mma writes the 128 x 128 Gram tile into TMEM (double-buffered), and 128 threads --
+// ONE THREAD PER QUERY ROW, the natural TMEM access pattern -- read their row with tcgen05.ld, turn each dot product
+// into the reference's FP32 score and feed an exact radix select: 4 passes of 8 bits over the order-preserving integer
+// image of the score, each pass a thread-private histogram in shared memory (no atomics, no inter-thread traffic),
+// each pass simply re-running the (cheap) tensor-core Gram.  A fifth pass collects the k winners, which one warp per
+// row then sorts with a register bitonic network.  Ties at the k-th score go to the lowest candidate index.
+//
+// Operands are FP16 hi/lo splits (22 significant bits, FP32 accumulation, Q_h X_h + Q_h X_l + Q_l X_h) of the inputs
+// scaled per cloud by a power of two that puts max|x| in [1024, 2048), so the Gram is FP32-faithful for any input
+// range; squared norms are FP32 from the unsplit values.
+#include "tc_common.cuh"
+
+namespace sed {
+
+enum { SEL_L2 = 0, SEL_PN = 1, SEL_COS = 2 };
+enum { OUT_IDX = 0, OUT_KTH = 1, OUT_TOP1 = 2 };
+
+constexpr int ST_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 select (thread per row, two groups)
+constexpr int ST_M = 128, ST_NC = 128;
+constexpr int ST_KMAX = 64;       // list capacity of the OUT_IDX mode
+
+struct SelParams {
+    const float* xxq; const float* xxc;   // squared norms (B, Npad) for L2 / PN (xxq == xxc for self-kNN)
+    const float* maxabs_q; const float* maxabs_c;  // per-cloud max|x| (operand scale); null -> fixed scale
+    float fixed_scale;
+    int Nq, Nc, npad, k;
+    const int* nc_ptr;                    // optional per-cloud candidate count
+    float W;
+    void* out_idx; int idx64;             // OUT_IDX: (B,Nq,k); OUT_TOP1: (B,Nq)
+    float* out_kth;                       // OUT_KTH: (B,Nq)
+};
+
+__host__ __device__ __forceinline__ float scale_from_maxabs(float m) {
+    // power of two s with s * m in [1024, 2048); 1 for empty / degenerate input
+    if (!(m > 0.f) || !(m < 3.0e38f)) return 1.0f;
+    int e;
+    frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)
+    e = 11 - e;
+    e = e < -60 ? -60 : (e > 60 ? 60 : e);
+    return ldexpf(1.0f, e);
+}
+
+template <int MODE>
+__device__ __forceinline__ float sel_score(float acc0, float acc1, float inv_s2, float xq, float xc, float W) {
+    if (MODE == SEL_L2) {
+        // src/PointNet.py:76-78: inner = -2 x.x' ; pd = (-xx_j - inner) - xx_i
+        const float dot = acc0 * inv_s2;
+        return __fsub_rn(fmaf(2.0f, dot, -xc), xq);
+    } else if (MODE == SEL_PN) {
+        // src/PointNet.py:112-120,128: p = (xx_j - 2 p.p') + xx_i ; n = 2 - 2 n.n' ; -(p * (1 + n * W))
+        const float pd = __fadd_rn(fmaf(-2.0f, acc0 * inv_s2, xc), xq);
+        const float nd = fmaf(-2.0f, acc1 * inv_s2, 2.0f);
+        return -__fmul_rn(pd, __fadd_rn(1.0f, __fmul_rn(nd, W)));
+    } else {
+        // src/mean_shift.py:130,146: dist = 2 - 2 x.y ; score = -dist
+        return -fmaf(-2.0f, acc0 * inv_s2, 2.0f);
+    }
+}
+
+// KB: 64-channel boxes per operand row (1: K <= 64, 2: K = 128).  RBITS: radix bits per pass.
+template <int MODE, int OUT, int KB, int RBITS>
+__global__ void __launch_bounds__(ST_THREADS, 1)
+select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
+                 const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, SelParams p) {
+    constexpr uint32_t PART_BYTES = KB * BOX_BYTES;
+    constexpr uint32_t TILE2 = 2 * PART_BYTES;                     // hi + lo
+    constexpr int STAGES = (KB == 1) ? 3 : 2;
+    constexpr int NBINS = 1 << RBITS;
+    constexpr int NPASS_RADIX = (OUT == OUT_TOP1) ? 0 : (32 + RBITS - 1) / RBITS;
+    constexpr int NPASS = (OUT == OUT_TOP1) ? 1 : NPASS_RADIX + (OUT == OUT_IDX ? 1 : 0);
+    constexpr uint32_t HIST_BYTES = NBINS * 128;                    // one group's u8 histogram
+    constexpr uint32_t SEL_BYTES = (OUT == OUT_TOP1) ? 1024 : 2 * HIST_BYTES;   // lists (48 KB) alias the histograms
+    static_assert(OUT != OUT_IDX || 2 * HIST_BYTES >= ST_KMAX * 128 * 6, "lists must fit in the histogram area");
+    constexpr int NACC = 2;   // PN: points / normals Grams; L2, COS: hi.hi and the cross terms (summed in FP32 RN by the
+                              // selection threads: the tensor core truncates when it accumulates, so the small terms
+                              // must not ride on the large accumulator)
+    constexpr uint32_t BUF_COLS = 128 * NACC;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw0 = smem_u32(smem_raw);
+    const uint32_t smem_base = (raw0 + 1023u) & ~1023u;
+    const uint32_t q_addr = smem_base;
+    const uint32_t x_addr = q_addr + TILE2;
+    const uint32_t sel_addr = x_addr + STAGES * TILE2;
+    const uint32_t bar_base = sel_addr + SEL_BYTES;
+    const uint32_t bar_q_full = bar_base;
+    const uint32_t bar_x_full = bar_base + 8;
+    const uint32_t bar_x_empty = bar_x_full + 8 * STAGES;
+    const uint32_t bar_s_full = bar_x_empty + 8 * STAGES;   // [2]
+    const uint32_t bar_s_empty = bar_s_full + 16;            // [2]
+    const uint32_t tmem_slot = bar_s_empty + 16;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw0));
+    uint8_t* sel_ptr = smem_raw + (sel_addr - raw0);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, q0 = blockIdx.x * ST_M;
+    const int Nc = p.nc_ptr ? min(max(p.nc_ptr[b], 0), p.Nc) : p.Nc;
+    const int T = (Nc + ST_NC - 1) / ST_NC;
+    const int J = T * NPASS;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_q_full, 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_empty + 8 * i, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ============================================================ TMA producer
+        if (lane == 0 && J > 0) {
+            mbar_expect_tx(bar_q_full, TILE2);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                tma_load_3d(q_addr + kb * BOX_BYTES, &map_qh, bar_q_full, kb * 64, q0, b);
+                tma_load_3d(q_addr + PART_BYTES + kb * BOX_BYTES, &map_ql, bar_q_full, kb * 64, q0, b);
+            }
+            for (int j = 0; j < J; ++j) {
+                const int s = j % STAGES, tile = j % T;
+                if (j >= STAGES) mbar_wait(bar_x_empty + 8 * s, ((j / STAGES) - 1) & 1);
+                const uint32_t dst = x_addr + s * TILE2, bar = bar_x_full + 8 * s;
+                mbar_expect_tx(bar, TILE2);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    tma_load_3d(dst + kb * BOX_BYTES, &map_xh, bar, kb * 64, tile * ST_NC, b);
+                    tma_load_3d(dst + PART_BYTES + kb * BOX_BYTES, &map_xl, bar, kb * 64, tile * ST_NC, b);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================================================ MMA issuer
+        if (lane == 0 && J > 0) {
+            constexpr uint32_t IDESC = make_idesc(0);
+            mbar_wait(bar_q_full, 0);
+            for (int j = 0; j < J; ++j) {
+                const int s = j % STAGES;
+                mbar_wait(bar_x_full + 8 * s, (j / STAGES) & 1);
+                if (j >= 2) mbar_wait(bar_s_empty + 8 * (j & 1), ((j >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint32_t xs = x_addr + s * TILE2;
+                const uint32_t d = tmem + (uint32_t)(j & 1) * BUF_COLS;
+                if (MODE == SEL_PN) {
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+                        // channels [0,16): points (3 used), [16,32): normals (3 used): one K-step each
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t qa = q_addr + ((term == 2) ? PART_BYTES : 0);   // Qh, Qh, Ql
+                            const uint32_t xb = xs + ((term == 1) ? PART_BYTES : 0);       // Xh, Xl, Xh
+                            umma_ss(d + a * 128, make_desc(qa + a * 32, 16), make_desc(xb + a * 32, 16), IDESC, term > 0);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t qa = q_addr + ((term == 2) ? PART_BYTES : 0);
+                        const uint32_t xb = xs + ((term == 1) ? PART_BYTES : 0);
+                        const uint32_t dd = d + (term == 0 ? 0u : 128u);                   // hi.hi | cross terms
+#pragma unroll
+                        for (int ks = 0; ks < KB * 4; ++ks) {
+                            const uint32_t off = (ks >> 2) * BOX_BYTES + (ks & 3) * 32;
+                            umma_ss(dd, make_desc(qa + off, 16), make_desc(xb + off, 16), IDESC,
+                                    (ks > 0 || term == 2) ? 1u : 0u);
+                        }
+                    }
+                }
+                tc_commit(bar_s_full + 8 * (j & 1));
+                tc_commit(bar_x_empty + 8 * s);
+            }
+        }
+    } else {
+        // ============================================================ selection: one thread per query row.
+        // Two groups of four warps; group g drains TMEM buffer g (tiles with j & 1 == g), each with its own histogram.
+        const int group = (warp - 2) >> 2;
+        const int quarter = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;
+        const int q = q0 + row;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const float sq = p.maxabs_q ? scale_from_maxabs(p.maxabs_q[b]) : p.fixed_scale;
+        const float sc = p.maxabs_c ? scale_from_maxabs(p.maxabs_c[b]) : p.fixed_scale;
+        const float inv_s2 = (1.0f / sq) * (1.0f / sc);
+        const float xq = (MODE == SEL_COS) ? 0.f : p.xxq[(long long)b * p.npad + min(q, p.npad - 1)];
+        const float* xxc = (MODE == SEL_COS) ? nullptr : p.xxc + (long long)b * p.npad;
+        // u8 saturating counters hist[g][bin][slot], slot = lane*4 + quarter: every lane of a warp on its own bank.
+        // Saturation at 255 is exact enough: bins ABOVE the one holding rank k_rem (<= 255) hold fewer than k_rem.
+        uint8_t* hist = sel_ptr + group * HIST_BYTES + lane * 4 + quarter;
+        const uint8_t* hist_o = sel_ptr + (group ^ 1) * HIST_BYTES + lane * 4 + quarter;
+        uint32_t* lkey = reinterpret_cast<uint32_t*>(sel_ptr) + row;                                   // lkey[pos * 128]
+        uint16_t* lidx = reinterpret_cast<uint16_t*>(sel_ptr + ST_KMAX * 128 * 4) + row;               // lidx[pos * 128]
+
+        uint32_t pref = 0;          // value of the key bits decided so far
+        int k_rem = p.k;            // rank still to be resolved inside the current prefix
+        int ties = 0, cnt = 0;      // collection pass
+        uint32_t best_key = 0; int best_idx = 0;   // OUT_TOP1
+        if (OUT != OUT_TOP1)
+            for (int i = 0; i < NBINS; ++i) hist[i * 128] = 0;
+
+        for (int j = 0; j < J; ++j) {
+            const int pass = j / T, tile = j - pass * T;
+            const bool radix = pass < NPASS_RADIX;
+            const bool mine = (OUT == OUT_IDX && !radix) ? (group == 0) : ((j & 1) == group);
+            const int known = pass * RBITS;                                   // key bits decided before this pass
+            const int shift = max(32 - known - RBITS, 0);
+            const int width = 32 - known - shift;
+            const uint32_t bmask = (1u << width) - 1u;
+            if (mine) {
+                const uint32_t sb = tmem + lane_addr + (uint32_t)(j & 1) * BUF_COLS;
+                const int nvalid = Nc - tile * ST_NC;                         // >= 128 except in the last tile
+                mbar_wait(bar_s_full + 8 * (j & 1), (j >> 1) & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(sb + c * 32, v0);
+                    tmem_ld32(sb + 128 + c * 32, v1);
+                    tmem_ld_wait();
+                    const int cbase = tile * ST_NC + c * 32;
+                    // ---- keys of the 32 candidates (independent: pipelines well)
+#pragma unroll
+                    for (int i4 = 0; i4 < 8; ++i4) {
+                        float4 xc4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (MODE != SEL_COS) xc4 = __ldg(reinterpret_cast<const float4*>(xxc + cbase + i4 * 4));
+                        const float xcs[4] = {xc4.x, xc4.y, xc4.z, xc4.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int i = i4 * 4 + e;
+                            const float a0 = __uint_as_float(v0[i]), a1 = __uint_as_float(v1[i]);
+                            const float s = (MODE == SEL_PN) ? sel_score<MODE>(a0, a1, inv_s2, xq, xcs[e], p.W)
+                                                             : sel_score<MODE>(__fadd_rn(a0, a1), 0.f, inv_s2, xq, xcs[e], p.W);
+                            v0[i] = f2ord(s);
+                        }
+                    }
+                    const int nv = nvalid - c * 32;                           // candidates i < nv of this chunk exist
+                    if (OUT == OUT_TOP1) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const bool gt = (i < nv) && (v0[i] > best_key);
+                            best_key = gt ? v0[i] : best_key;
+                            best_idx = gt ? cbase + i : best_idx;
+                        }
+                    } else if (radix && pass < 2) {
+                        // dense passes: nearly every candidate shares the leading bits -> unconditional read-modify-write,
+                        // four candidates at a time with duplicates of a bin resolved in registers
+#pragma unroll
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            uint32_t bn[4], m[4], cn[4];
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int i = i4 * 4 + e;
+                                const uint32_t key = v0[i];
+                                bn[e] = (key >> shift) & bmask;
+                                m[e] = ((i < nv) && (known == 0 || (key >> (32 - known)) == pref)) ? 1u : 0u;
+                                cn[e] = hist[bn[e] * 128];
+                            }
+                            const uint32_t n0 = min(cn[0] + m[0], 255u);
+                            cn[1] = (bn[1] == bn[0]) ? n0 : cn[1];
+                            const uint32_t n1 = min(cn[1] + m[1], 255u);
+                            cn[2] = (bn[2] == bn[1]) ? n1 : ((bn[2] == bn[0]) ? n0 : cn[2]);
+                            const uint32_t n2 = min(cn[2] + m[2], 255u);
+                            cn[3] = (bn[3] == bn[2]) ? n2 : ((bn[3] == bn[1]) ? n1 : ((bn[3] == bn[0]) ? n0 : cn[3]));
+                            const uint32_t n3 = min(cn[3] + m[3], 255u);
+                            hist[bn[0] * 128] = (uint8_t)n0;
+                            hist[bn[1] * 128] = (uint8_t)n1;
+                            hist[bn[2] * 128] = (uint8_t)n2;
+                            hist[bn[3] * 128] = (uint8_t)n3;
+                        }
+                    } else if (radix) {
+                        // sparse passes: few candidates still match the prefix
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t key = v0[i];
+                            if ((i < nv) && (key >> (32 - known)) == pref) {
+                                const uint32_t bin = (key >> shift) & bmask;
+                                hist[bin * 128] = (uint8_t)min((uint32_t)hist[bin * 128] + 1u, 255u);
+                            }
+                        }
+                    } else {
+                        // collection: everything above the k-th key, then ties in index order
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const uint32_t key = v0[i];
+                            if ((i < nv) && key >= pref) {
+                                const bool take = key > pref || ties < k_rem;
+                                if (take) {
+                                    if (key == pref) ++ties;
+                                    if (cnt < ST_KMAX) { lkey[cnt * 128] = key; lidx[cnt * 128] = (uint16_t)(cbase + i); }
+                                    ++cnt;
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(bar_s_empty + 8 * (j & 1));
+            }
+            if (OUT != OUT_TOP1 && radix && tile == T - 1) {
+                // end of a radix pass: both groups' histograms are complete -> locate the bin holding rank k_rem
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                int cum = 0, sel = 0;
+                bool found = false;
+                for (int bin = (int)bmask; bin >= 0; --bin) {
+                    const int cbin = (int)hist[bin * 128] + (int)hist_o[bin * 128];
+                    if (!found) {
+                        if (cum + cbin >= k_rem) { sel = bin; found = true; }
+                        else cum += cbin;
+                    }
+                }
+                pref = (pref << width) | (uint32_t)sel;
+                k_rem -= cum;
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // everyone has read both histograms
+                // (the collection lists alias the histograms: nobody appends before this point)
+                if (pass + 1 < NPASS_RADIX)
+                    for (int bin = 0; bin < NBINS; ++bin) hist[bin * 128] = 0;
+            }
+        }
+
+        // ---- results
+        if (OUT == OUT_KTH) {
+            if (group == 0 && q < p.Nq) p.out_kth[(long long)b * p.Nq + q] = ord2f(pref);
+        } else if (OUT == OUT_TOP1) {
+            // merge the two groups' candidates (lower index wins ties)
+            unsigned long long* slot = reinterpret_cast<unsigned long long*>(sel_ptr) + row;
+            const unsigned long long mineK = ((unsigned long long)best_key << 32) | (0xFFFFFFFFu - (uint32_t)best_idx);
+            if (group == 1) *slot = mineK;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (group == 0 && q < p.Nq) {
+                const unsigned long long o = *slot;
+                const unsigned long long best = o > mineK ? o : mineK;
+                const int bi = (best >> 32) ? (int)(0xFFFFFFFFu - (uint32_t)(best & 0xFFFFFFFFull)) : 0;
+                if (p.idx64) reinterpret_cast<long long*>(p.out_idx)[(long long)b * p.Nq + q] = bi;
+                else reinterpret_cast<int*>(p.out_idx)[(long long)b * p.Nq + q] = bi;
+            }
+        } else {
+            // one warp per row: bitonic sort (descending score, ascending index) of the k collected entries;
+            // the lists were written by group 0, both groups sort (16 rows per warp)
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const int k = p.k;
+            for (int r = group * 16; r < group * 16 + 16; ++r) {
+                const int rr = quarter * 32 + r;
+                const int qq = q0 + rr;
+                if (qq >= p.Nq) break;
+                const uint32_t* rk = reinterpret_cast<const uint32_t*>(sel_ptr) + rr;
+                const uint16_t* ri = reinterpret_cast<const uint16_t*>(sel_ptr + ST_KMAX * 128 * 4) + rr;
+                unsigned long long e[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pos = lane + 32 * h;
+                    e[h] = (pos < k) ? (((unsigned long long)rk[pos * 128] << 32) | (0xFFFFFFFFu - (uint32_t)ri[pos * 128])) : 0ull;
+                }
+#pragma unroll
+                for (int k2 = 2; k2 <= 64; k2 <<= 1) {
+#pragma unroll
+                    for (int jj = k2 >> 1; jj > 0; jj >>= 1) {
+                        if (jj == 32) {
+                            // partner is the other element of this lane; final merge: descending
+                            if (e[0] < e[1]) { const unsigned long long t = e[0]; e[0] = e[1]; e[1] = t; }
+                        } else {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const int i = lane + 32 * h;
+                                const unsigned long long o = shfl_xor_u64(e[h], jj);
+                                const bool desc = ((i & k2) == 0);          // block direction (k2 == 64: all descending)
+                                const bool lower = ((i & jj) == 0);         // this element sits at the lower index
+                                const bool keep_max = (desc == lower);
+                                e[h] = keep_max ? (e[h] > o ? e[h] : o) : (e[h] < o ? e[h] : o);
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pos = lane + 32 * h;
+                    if (pos < k) {
+                        const int idx = (int)(0xFFFFFFFFu - (uint32_t)(e[h] & 0xFFFFFFFFull));
+                        const long long o = ((long long)b * p.Nq + qq) * k + pos;
+                        if (p.idx64) reinterpret_cast<long long*>(p.out_idx)[o] = idx;
+                        else reinterpret_cast<int*>(p.out_idx)[o] = idx;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- operand packing
+__global__ void maxabs_kernel(const float* __restrict__ x, long long bstride, long long n, float* __restrict__ out) {
+    const int b = blockIdx.y;
+    const float* xb = x + (long long)b * bstride;
+    float m = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(xb[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out + b), __float_as_uint(m));
+}
+
+// channel-major x (B,C,N) -> fp16 hi/lo rows [B][N][64] (scaled), FP32 squared norms (B,npad).
+// pn: channels 0-2 -> slots 0-2 (points), 3-5 -> slots 16-18 (normals); norms over the points only.
+__global__ void pack_cm_kernel(const float* __restrict__ x, long long bstride, int C, int N, int npad, int pn,
+                               const float* __restrict__ maxabs, __half* __restrict__ hi, __half* __restrict__ lo,
+                               float* __restrict__ xx) {
+    const int b = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= npad) return;
+    if (n >= N) { xx[(long long)b * npad + n] = 0.f; return; }
+    const float s = scale_from_maxabs(maxabs[b]);
+    const float* xb = x + (long long)b * bstride + n;
+    __half* ho = hi + ((long long)b * N + n) * 64;
+    __half* lw = lo + ((long long)b * N + n) * 64;
+    float nrm = 0.f;
+#pragma unroll 1
+    for (int g = 0; g < 8; ++g) {
+        __align__(16) __half h[8];
+        __align__(16) __half l[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int slot = g * 8 + e;
+            int c = slot;
+            if (pn) c = (slot < 3) ? slot : ((slot >= 16 && slot < 19) ? slot - 13 : -1);
+            float v = (c >= 0 && c < C) ? xb[(long long)c * N] : 0.f;
+            if (c >= 0 && c < C && (!pn || c < 3)) nrm = fmaf(v, v, nrm);
+            v *= s;
+            h[e] = __float2half_rn(v);
+            l[e] = __float2half_rn(v - __half2float(h[e]));
+        }
+        *reinterpret_cast<uint4*>(ho + g * 8) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(lw + g * 8) = *reinterpret_cast<const uint4*>(l);
+    }
+    xx[(long long)b * npad + n] = nrm;
+}
+
+// row-major x (B,N,d) d <= 128 -> fp16 hi/lo rows [B][N][128] scaled by `scale`
+__global__ void pack_rm_kernel(const float* __restrict__ x, long long rows, int d, float scale, __half* __restrict__ hi,
+                               __half* __restrict__ lo) {
+    const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane * 4 < d) v = *reinterpret_cast<const float4*>(x + row * d + lane * 4);
+    const float a[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+    __align__(8) __half h[4];
+    __align__(8) __half l[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        h[e] = __float2half_rn(a[e]);
+        l[e] = __float2half_rn(a[e] - __half2float(h[e]));
+    }
+    *reinterpret_cast<uint2*>(hi + row * 128 + lane * 4) = *reinterpret_cast<const uint2*>(h);
+    *reinterpret_cast<uint2*>(lo + row * 128 + lane * 4) = *reinterpret_cast<const uint2*>(l);
+}
+
+template <int MODE, int OUT, int KB, int RBITS>
+static int launch_select(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& xh, const CUtensorMap& xl,
+                         const SelParams& p, int B, cudaStream_t st) {
+    constexpr int STAGES = (KB == 1) ? 3 : 2;
+    constexpr int NBINS = 1 << RBITS;
+    constexpr size_t SEL = (OUT == OUT_TOP1) ? 1024 : (size_t)2 * NBINS * 128;
+    constexpr size_t smem = (size_t)(STAGES + 1) * 2 * KB * BOX_BYTES + SEL + 1024 + 256;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    auto kern = select_tc_kernel<MODE, OUT, KB, RBITS>;
+    SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.Nq + ST_M - 1) / ST_M, B);
+    kern<<<grid, ST_THREADS, smem, st>>>(qh, ql, xh, xl, p);
+    SED_CHECK_LAUNCH();
+    return SED_OK;
+}
+
+// kNN over channel-major features: metric L2 (pn = 0) or point x normal (pn = 1).  k <= 64, C <= 64, N < 65536.
+int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn, float W, void* idx, int idx64,
+           cudaStream_t st) {
+    if (k > ST_KMAX || C > 64 || N >= 65536 || N < k || (pn && C != 6)) return SED_ERR_UNSUPPORTED;
+    const int npad = (N + 127) / 128 * 128;
+    const size_t rows = (size_t)B * N;
+    ensure_pool_config();
+    char* buf = nullptr;
+    const size_t bytes_h = rows * 64 * sizeof(__half);
+    SED_CUDA(cudaMallocAsync((void**)&buf, 2 * bytes_h + (size_t)B * npad * 4 + 256, st));
+    __half* hi = (__half*)buf;
+    __half* lo = (__half*)(buf + bytes_h);
+    float* xx = (float*)(buf + 2 * bytes_h);
+    float* mx = xx + (size_t)B * npad;
+    int rc = SED_OK;
+    if (cudaMemsetAsync(mx, 0, B * sizeof(float), st) != cudaSuccess) rc = SED_ERR_CUDA_BASE - 1;
+    if (rc == SED_OK) {
+        maxabs_kernel<<<dim3(64, B), 256, 0, st>>>(x, bstride, (long long)C * N, mx);
+        pack_cm_kernel<<<dim3((npad + 127) / 128, B), 128, 0, st>>>(x, bstride, C, N, npad, pn, mx, hi, lo, xx);
+        g_sed_launches += 2;
+        CUtensorMap mh, ml;
+        rc = make_map_f16(&mh, hi, B, N, 64);
+        if (rc == SED_OK) rc = make_map_f16(&ml, lo, B, N, 64);
+        SelParams p{xx, xx, mx, mx, 1.0f, N, N, npad, k, nullptr, W, idx, idx64, nullptr};
+        if (rc == SED_OK)
+            rc = pn ? launch_select<SEL_PN, OUT_IDX, 1, 8>(mh, ml, mh, ml, p, B, st)
+                    : launch_select<SEL_L2, OUT_IDX, 1, 8>(mh, ml, mh, ml, p, B, st);
+    }
+    cudaFreeAsync(buf, st);
+    return rc;
+}
+
+// Cosine scores between unit rows: Q (B,Nq,d), Cand (B,Nc,d) row-major, d <= 128 (multiple of 4).
+//   kth_out != null : K-th largest score (-dist) of every row (Q == Cand)           -> compute_bandwidth
+//   idx_out != null : index of the best candidate of every row (first on ties)       -> nms membership / labels
+int cos_select_tc(const float* Q, const float* Cand, int B, int Nq, int Nc, const int* nc_ptr, int d, int K,
+                  float* kth_out, void* idx_out, int idx64, cudaStream_t st) {
+    if (d > 128 || (d & 3) || Nc >= 65536 || (kth_out && (K > Nc || K <= 0 || K > 255))) return SED_ERR_UNSUPPORTED;
+    const bool same = (Q == Cand && Nq == Nc);
+    const size_t rq = (size_t)B * Nq, rc_ = (size_t)B * Nc;
+    const size_t bytes_q = rq * 128 * sizeof(__half), bytes_c = rc_ * 128 * sizeof(__half);
+    ensure_pool_config();
+    char* buf = nullptr;
+    SED_CUDA(cudaMallocAsync((void**)&buf, 2 * bytes_q + (same ? 0 : 2 * bytes_c), st));
+    __half *qh = (__half*)buf, *ql = (__half*)(buf + bytes_q);
+    __half *ch = same ? qh : (__half*)(buf + 2 * bytes_q), *cl = same ? ql : (__half*)(buf + 2 * bytes_q + bytes_c);
+    const float scale = 8.0f;
+    pack_rm_kernel<<<(unsigned)((rq + 7) / 8), 256, 0, st>>>(Q, (long long)rq, d, scale, qh, ql);
+    ++g_sed_launches;
+    if (!same) {
+        pack_rm_kernel<<<(unsigned)((rc_ + 7) / 8), 256, 0, st>>>(Cand, (long long)rc_, d, scale, ch, cl);
+        ++g_sed_launches;
+    }
+    CUtensorMap mqh, mql, mch, mcl;
+    int rc = make_map_f16(&mqh, qh, B, Nq, 128);
+    if (rc == SED_OK) rc = make_map_f16(&mql, ql, B, Nq, 128);
+    if (rc == SED_OK) rc = make_map_f16(&mch, ch, B, Nc, 128);
+    if (rc == SED_OK) rc = make_map_f16(&mcl, cl, B, Nc, 128);
+    SelParams p{nullptr, nullptr, nullptr, nullptr, scale, Nq, Nc, 0, K, nc_ptr, 0.f, idx_out, idx64, kth_out};
+    if (rc == SED_OK)
+        rc = kth_out ? launch_select<SEL_COS, OUT_KTH, 2, 7>(mqh, mql, mch, mcl, p, B, st)
+                     : launch_select<SEL_COS, OUT_TOP1, 2, 8>(mqh, mql, mch, mcl, p, B, st);
+    cudaFreeAsync(buf, st);
+    return rc;
+}
+
+}  // namespace sed
