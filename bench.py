@@ -265,7 +265,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--prec", type=int, default=int(os.environ.get("SEDNET_B200_MS_PREC", "0")))
+    ap.add_argument("--prec", type=int, default=int(os.environ.get("SEDNET_B200_MS_PREC", "1")))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

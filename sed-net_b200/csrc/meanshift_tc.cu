@@ -24,7 +24,7 @@ namespace sed {
 constexpr int TC_M = 128;        // query rows per CTA  (UMMA M)
 constexpr int TC_NK = 128;       // keys per tile        (UMMA N of S, K of PV)
 constexpr int TC_D = 128;        // channels             (K of S, N of PV)
-constexpr int TC_THREADS = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 exp/epilogue
+constexpr int TC_THREADS = 320;  // warp 0 TMA, warp 1 MMA, warps 2-9 exp/epilogue (two groups of four)
 constexpr int TILE_BYTES = 2 * BOX_BYTES;       // 128 rows x 128 fp16
 constexpr float kOperandScale = 8.0f;
 
@@ -158,7 +158,10 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_cons
             tc_commit(bar_o_full);
         }
     } else {
-        // ============================================================ exp warps (4 x 32 rows) + epilogue
+        // ============================================================ exp warps + epilogue.  Two groups of 4 x 32
+        // rows: group g turns S into P for the tiles living in TMEM buffer g (j & 1 == g), so the exp work of two
+        // consecutive tiles overlaps and the tensor pipe is not left waiting for P.
+        const int group = (warp - 2) >> 2;
         const int quarter = warp & 3;                       // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;                // query row within the tile
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -170,7 +173,7 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_cons
         // epanechnikov: 0.75 * (1 - (2 - 2s)/b^2) = S_acc * e1 + e0
         const float e1 = 1.5f * inv_b2 / (kOperandScale * kOperandScale);
         const float e0 = 0.75f - 1.5f * inv_b2;
-        for (int j = 0; j < T; ++j) {
+        for (int j = group; j < T; j += 2) {
             const uint32_t sb = tmem + lane_addr + (uint32_t)(j & 1) * 128u;
             mbar_wait(bar_s_full + 8 * (j & 1), (j >> 1) & 1);
             tc_fence_after();
@@ -203,20 +206,26 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_cons
         mbar_wait(bar_o_full, 0);
         tc_fence_after();
         const uint32_t ob = tmem + lane_addr + 256u;
+        // each group owns two of the four 32-channel chunks; the squared norm is exchanged through shared memory
         float ss = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = group * 2 + cc;
             uint32_t v[32];
             tmem_ld32(ob + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) { const float o = __uint_as_float(v[i]); ss = fmaf(o, o, ss); }
         }
-        const float rn = 1.0f / sqrtf(ss);
+        float* ssx = reinterpret_cast<float*>(smem_raw + (q_addr - smem_u32(smem_raw)));   // Q tile is dead by now
+        ssx[group * 128 + row] = ss;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float rn = 1.0f / sqrtf(ssx[row] + ssx[128 + row]);
         const int q = q0 + row;
         const long long rowoff = ((long long)b * N + q) * TC_D;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int cc = 0; cc < 2; ++cc) {
+            const int c = group * 2 + cc;
             uint32_t v[32];
             tmem_ld32(ob + c * 32, v);
             tmem_ld_wait();
