@@ -16,6 +16,9 @@
 // Operands are FP16 hi/lo splits (22 significant bits, FP32 accumulation, Q_h X_h + Q_h X_l + Q_l X_h) of the inputs
 // scaled per cloud by a power of two that puts max|x| in [1024, 2048), so the Gram is FP32-faithful for any input
 // range; squared norms are FP32 from the unsplit values.
+#include <stdlib.h>
+#include <string.h>
+
 #include "tc_common.cuh"
 
 namespace sed {
@@ -403,6 +406,314 @@ select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_consta
     }
 }
 
+// ---------------------------------------------------------------------------------------------- streaming top-k
+// Single-pass variant for k <= 64 (the kNN graph of the encoder): the Gram runs ONCE.  Each query row is owned by
+// one thread that keeps, in shared memory, a private candidate buffer of SS_CAP (score, index) entries and a
+// threshold register: a candidate is appended iff its score beats the threshold (predicated stores, no divergence).
+// When any buffer of the warp is about to overflow, every lane prunes its own buffer: a bisection over the
+// order-preserving integer image of the scores finds a pivot that keeps between k and k + SS_WIN entries, the buffer is
+// compacted in place (index order preserved, so ties keep going to the lowest index) and the pivot becomes the new
+// threshold.  A threshold only has to guarantee that >= k earlier candidates are at least as good, so the prune need
+// not be exact; the final prune (window 0) is, and the k survivors of a row are sorted by one warp.
+// Expected appends per row ~ k ln(N/k) (a few hundred of 10 000 candidates); ~6 prunes per row.
+constexpr int SS_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 select (thread per row)
+constexpr int SS_CAP = 168;       // entries per row buffer
+constexpr int SS_WIN = 24;        // a prune leaves between k and k + SS_WIN entries
+constexpr int SS_STAGES = 2;
+struct SelTrue { static constexpr bool value = true; };
+struct SelFalse { static constexpr bool value = false; };
+
+template <int MODE>
+__global__ void __launch_bounds__(SS_THREADS, 1)
+select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
+                     const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, SelParams p) {
+    constexpr uint32_t PART_BYTES = BOX_BYTES;                     // 128 rows x 64 channels fp16
+    constexpr uint32_t TILE2 = 2 * PART_BYTES;                     // hi + lo
+    constexpr uint32_t KEY_BYTES = SS_CAP * 128 * 4, IDX_BYTES = SS_CAP * 128 * 2;
+    constexpr uint32_t BUF_COLS = 256;                             // two 128-column accumulators per TMEM buffer
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw0 = smem_u32(smem_raw);
+    const uint32_t smem_base = (raw0 + 1023u) & ~1023u;
+    const uint32_t q_addr = smem_base;
+    const uint32_t x_addr = q_addr + TILE2;
+    const uint32_t list_addr = x_addr + SS_STAGES * TILE2;
+    const uint32_t bar_base = list_addr + KEY_BYTES + IDX_BYTES;
+    const uint32_t bar_q_full = bar_base;
+    const uint32_t bar_x_full = bar_base + 8;
+    const uint32_t bar_x_empty = bar_x_full + 8 * SS_STAGES;
+    const uint32_t bar_s_full = bar_x_empty + 8 * SS_STAGES;   // [2]
+    const uint32_t bar_s_empty = bar_s_full + 16;              // [2]
+    const uint32_t tmem_slot = bar_s_empty + 16;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw0));
+    uint8_t* list_ptr = smem_raw + (list_addr - raw0);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, q0 = blockIdx.x * ST_M;
+    const int Nc = p.Nc;
+    const int T = (Nc + ST_NC - 1) / ST_NC;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_q_full, 1);
+        for (int s = 0; s < SS_STAGES; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_empty + 8 * i, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ============================================================ TMA producer
+        if (lane == 0) {
+            mbar_expect_tx(bar_q_full, TILE2);
+            tma_load_3d(q_addr, &map_qh, bar_q_full, 0, q0, b);
+            tma_load_3d(q_addr + PART_BYTES, &map_ql, bar_q_full, 0, q0, b);
+            for (int j = 0; j < T; ++j) {
+                const int s = j % SS_STAGES;
+                if (j >= SS_STAGES) mbar_wait(bar_x_empty + 8 * s, ((j / SS_STAGES) - 1) & 1);
+                const uint32_t dst = x_addr + s * TILE2, bar = bar_x_full + 8 * s;
+                mbar_expect_tx(bar, TILE2);
+                tma_load_3d(dst, &map_xh, bar, 0, j * ST_NC, b);
+                tma_load_3d(dst + PART_BYTES, &map_xl, bar, 0, j * ST_NC, b);
+            }
+        }
+    } else if (warp == 1) {
+        // ============================================================ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t IDESC = make_idesc(0);
+            mbar_wait(bar_q_full, 0);
+            for (int j = 0; j < T; ++j) {
+                const int s = j % SS_STAGES;
+                mbar_wait(bar_x_full + 8 * s, (j / SS_STAGES) & 1);
+                if (j >= 2) mbar_wait(bar_s_empty + 8 * (j & 1), ((j >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint32_t xs = x_addr + s * TILE2;
+                const uint32_t d = tmem + (uint32_t)(j & 1) * BUF_COLS;
+                if (MODE == SEL_PN) {
+#pragma unroll
+                    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {
+                            const uint32_t qa = q_addr + ((term == 2) ? PART_BYTES : 0);   // Qh, Qh, Ql
+                            const uint32_t xb = xs + ((term == 1) ? PART_BYTES : 0);       // Xh, Xl, Xh
+                            umma_ss(d + a * 128, make_desc(qa + a * 32, 16), make_desc(xb + a * 32, 16), IDESC, term > 0);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t qa = q_addr + ((term == 2) ? PART_BYTES : 0);
+                        const uint32_t xb = xs + ((term == 1) ? PART_BYTES : 0);
+                        const uint32_t dd = d + (term == 0 ? 0u : 128u);                   // hi.hi | cross terms
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks)
+                            umma_ss(dd, make_desc(qa + ks * 32, 16), make_desc(xb + ks * 32, 16), IDESC,
+                                    (ks > 0 || term == 2) ? 1u : 0u);
+                    }
+                }
+                tc_commit(bar_s_full + 8 * (j & 1));
+                tc_commit(bar_x_empty + 8 * s);
+            }
+        }
+    } else {
+        // ============================================================ selection: one thread per query row
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int q = q0 + row;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const float sq = scale_from_maxabs(p.maxabs_q[b]);
+        const float sc = scale_from_maxabs(p.maxabs_c[b]);
+        const float inv2 = 2.0f * ((1.0f / sq) * (1.0f / sc));          // power of two: products below are exact
+        const float xq = p.xxq[(long long)b * p.npad + min(q, p.npad - 1)];
+        const float* xxc = p.xxc + (long long)b * p.npad;
+        const float W = p.W;
+        const int k = p.k;
+        uint32_t* lkey = reinterpret_cast<uint32_t*>(list_ptr) + row;                      // lkey[pos * 128]
+        uint16_t* lidx = reinterpret_cast<uint16_t*>(list_ptr + KEY_BYTES) + row;          // lidx[pos * 128]
+        float thr = -INFINITY;
+        int cnt = 0;
+
+        // keeps between k and k + win entries (exactly min(cnt, k) for win == 0); thr <- pivot
+        auto prune = [&](int win) {
+            const bool active = cnt > k + win;
+            float lo_f = thr;
+            if (active) {
+                float mx = -INFINITY, mn = INFINITY;
+                for (int i = 0; i < cnt; ++i) {
+                    const float v = __uint_as_float(lkey[i * 128]);
+                    mx = fmaxf(mx, v); mn = fminf(mn, v);
+                }
+                if (!(lo_f > -INFINITY)) lo_f = mn;
+                // invariant: count(>= lo) >= k, count(>= hi) < k (hi starts one step above the maximum)
+                uint32_t lo_u = f2ord(lo_f), hi_u = f2ord(mx) + 1u;
+                int c_lo = cnt;
+                while (c_lo > k + win && hi_u - lo_u > 1u) {
+                    const uint32_t mid_u = lo_u + ((hi_u - lo_u) >> 1);
+                    const float mid_f = ord2f(mid_u);
+                    int c = 0;
+                    for (int i = 0; i < cnt; ++i) c += (__uint_as_float(lkey[i * 128]) >= mid_f) ? 1 : 0;
+                    if (c >= k) { lo_u = mid_u; lo_f = mid_f; c_lo = c; }
+                    else hi_u = mid_u;
+                }
+                int g = 0;
+                for (int i = 0; i < cnt; ++i) g += (__uint_as_float(lkey[i * 128]) > lo_f) ? 1 : 0;
+                const int quota = max(k - g, 0);
+                int w = 0, t = 0;
+                for (int r = 0; r < cnt; ++r) {
+                    const uint32_t kv = lkey[r * 128];
+                    const uint16_t iv = lidx[r * 128];
+                    const float v = __uint_as_float(kv);
+                    const bool tie = (v == lo_f);
+                    const bool keep = (v > lo_f) || (tie && t < quota);
+                    t += tie ? 1 : 0;
+                    if (keep) { lkey[w * 128] = kv; lidx[w * 128] = iv; ++w; }
+                }
+                cnt = w;
+                thr = lo_f;
+            }
+            __syncwarp();
+        };
+
+        // one 32-candidate chunk of this thread's row
+        auto process_t = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int cbase, int nv, auto tail) {
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 xc4 = __ldg(reinterpret_cast<const float4*>(xxc + cbase + i4 * 4));
+                const float xcs[4] = {xc4.x, xc4.y, xc4.z, xc4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = i4 * 4 + e;
+                    const float a0 = __uint_as_float(v0[i]), a1 = __uint_as_float(v1[i]);
+                    float s;
+                    if (MODE == SEL_PN) {
+                        // src/PointNet.py:112-120,128: p = (xx_j - 2 p.p') + xx_i ; n = 2 - 2 n.n' ; -(p * (1 + n * W))
+                        const float pd = __fadd_rn(fmaf(-inv2, a0, xcs[e]), xq);
+                        const float nd = fmaf(-inv2, a1, 2.0f);
+                        s = -__fmul_rn(pd, __fadd_rn(1.0f, __fmul_rn(nd, W)));
+                    } else {
+                        // src/PointNet.py:76-78: inner = -2 x.x' ; pd = (-xx_j - inner) - xx_i
+                        s = __fsub_rn(fmaf(inv2, __fadd_rn(a0, a1), -xcs[e]), xq);
+                    }
+                    const bool pass = decltype(tail)::value ? ((s > thr) && (i < nv)) : (s > thr);
+                    if (pass) {
+                        lkey[cnt * 128] = __float_as_uint(s);
+                        lidx[cnt * 128] = (uint16_t)(cbase + i);
+                        ++cnt;
+                    }
+                }
+            }
+        };
+        auto process = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int cbase, int nv) {
+            if (nv >= 32) process_t(v0, v1, cbase, nv, SelFalse{});   // warp-uniform: every tile but the last
+            else process_t(v0, v1, cbase, nv, SelTrue{});
+        };
+
+        for (int j = 0; j < T; ++j) {
+            const uint32_t sb = tmem + lane_addr + (uint32_t)(j & 1) * BUF_COLS;
+            const int nvalid = Nc - j * ST_NC;                         // >= 128 except in the last tile
+            mbar_wait(bar_s_full + 8 * (j & 1), (j >> 1) & 1);
+            tc_fence_after();
+            uint32_t a0[32], a1[32], b0[32], b1[32];
+            tmem_ld32(sb, a0);
+            tmem_ld32(sb + 128, a1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 4; c += 2) {
+                // chunk c from (a0, a1) while chunk c + 1 loads into (b0, b1), then the other way round
+                tmem_ld32(sb + (c + 1) * 32, b0);
+                tmem_ld32(sb + 128 + (c + 1) * 32, b1);
+                if (__any_sync(0xffffffffu, cnt > SS_CAP - 32)) prune(SS_WIN);
+                process(a0, a1, j * ST_NC + c * 32, nvalid - c * 32);
+                tmem_ld_wait();
+                if (c + 2 < 4) {
+                    tmem_ld32(sb + (c + 2) * 32, a0);
+                    tmem_ld32(sb + 128 + (c + 2) * 32, a1);
+                }
+                if (__any_sync(0xffffffffu, cnt > SS_CAP - 32)) prune(SS_WIN);
+                process(b0, b1, j * ST_NC + (c + 1) * 32, nvalid - (c + 1) * 32);
+                tmem_ld_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(bar_s_empty + 8 * (j & 1));
+        }
+
+        // ---- exact top-k of the survivors, then one warp sorts each of its 32 rows
+        prune(0);
+        __syncwarp();
+        // per-row survivor counts (normally k) through shuffles: the sorter of row r asks lane r
+        for (int r = 0; r < 32; ++r) {
+            const int rr = quarter * 32 + r;
+            const int qq = q0 + rr;
+            const int rcnt = __shfl_sync(0xffffffffu, cnt, r);
+            if (qq >= p.Nq) break;
+            const uint32_t* rk = reinterpret_cast<const uint32_t*>(list_ptr) + rr;
+            const uint16_t* ri = reinterpret_cast<const uint16_t*>(list_ptr + KEY_BYTES) + rr;
+            unsigned long long e[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int pos = lane + 32 * h;
+                e[h] = (pos < rcnt) ? (((unsigned long long)f2ord(__uint_as_float(rk[pos * 128])) << 32) |
+                                       (0xFFFFFFFFu - (uint32_t)ri[pos * 128]))
+                                    : 0ull;
+            }
+#pragma unroll
+            for (int k2 = 2; k2 <= 64; k2 <<= 1) {
+#pragma unroll
+                for (int jj = k2 >> 1; jj > 0; jj >>= 1) {
+                    if (jj == 32) {
+                        if (e[0] < e[1]) { const unsigned long long t = e[0]; e[0] = e[1]; e[1] = t; }
+                    } else {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int i = lane + 32 * h;
+                            const unsigned long long o = shfl_xor_u64(e[h], jj);
+                            const bool desc = ((i & k2) == 0);
+                            const bool lower = ((i & jj) == 0);
+                            const bool keep_max = (desc == lower);
+                            e[h] = keep_max ? (e[h] > o ? e[h] : o) : (e[h] < o ? e[h] : o);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int pos = lane + 32 * h;
+                if (pos < k) {
+                    const int idx = (e[h] >> 32) ? (int)(0xFFFFFFFFu - (uint32_t)(e[h] & 0xFFFFFFFFull)) : 0;
+                    const long long o = ((long long)b * p.Nq + qq) * k + pos;
+                    if (p.idx64) reinterpret_cast<long long*>(p.out_idx)[o] = idx;
+                    else reinterpret_cast<int*>(p.out_idx)[o] = idx;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+template <int MODE>
+static int launch_stream(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& xh, const CUtensorMap& xl,
+                         const SelParams& p, int B, cudaStream_t st) {
+    constexpr size_t smem = (size_t)(SS_STAGES + 1) * 2 * BOX_BYTES + (size_t)SS_CAP * 128 * 6 + 1024 + 256;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    auto kern = select_stream_kernel<MODE>;
+    SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.Nq + ST_M - 1) / ST_M, B);
+    kern<<<grid, SS_THREADS, smem, st>>>(qh, ql, xh, xl, p);
+    SED_CHECK_LAUNCH();
+    return SED_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- operand packing
 __global__ void maxabs_kernel(const float* __restrict__ x, long long bstride, long long n, float* __restrict__ out) {
     const int b = blockIdx.y;
@@ -509,9 +820,13 @@ int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn
         rc = make_map_f16(&mh, hi, B, N, 64);
         if (rc == SED_OK) rc = make_map_f16(&ml, lo, B, N, 64);
         SelParams p{xx, xx, mx, mx, 1.0f, N, N, npad, k, nullptr, W, idx, idx64, nullptr};
-        if (rc == SED_OK)
+        // SEDNET_B200_KNN=radix selects the multi-pass radix kernel (A/B comparisons); default: single-pass streaming
+        static const bool radix = [] { const char* e = getenv("SEDNET_B200_KNN"); return e && !strcmp(e, "radix"); }();
+        if (rc == SED_OK && radix)
             rc = pn ? launch_select<SEL_PN, OUT_IDX, 1, 8>(mh, ml, mh, ml, p, B, st)
                     : launch_select<SEL_L2, OUT_IDX, 1, 8>(mh, ml, mh, ml, p, B, st);
+        else if (rc == SED_OK)
+            rc = pn ? launch_stream<SEL_PN>(mh, ml, mh, ml, p, B, st) : launch_stream<SEL_L2>(mh, ml, mh, ml, p, B, st);
     }
     cudaFreeAsync(buf, st);
     return rc;
