@@ -14,6 +14,8 @@
 // operand is split x*8 = hi + lo (hi = fp16(8x), lo = fp16(8x - hi): 22 significant bits, lo may be subnormal,
 // which costs nothing in absolute error) and
 //     prec_mode 1:  S = Qh Xh + Qh Xl + Ql Xh   (3 MMAs),   O = Ph Xh + Ph Xl   (2 MMAs)
+//     prec_mode 3:  S = Qh Xh + Qh Xl + Ql Xh   (3 MMAs),   O = Ph Xh           (P is FP16 anyway: the X_l term of O
+//                   only removes an unbiased 2^-12 relative rounding of X that averages out over the cluster)
 //     prec_mode 2:  S = Qh Xh,                               O = Ph Xh           (fast)
 // The scale 8 keeps hi/lo away from the bottom of the FP16 range; 64 = 8*8 is folded into the exp2 argument and
 // the factor 8 on O vanishes in the normalisation.
@@ -301,7 +303,7 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
                 float* out, float* tmp, cudaStream_t st) {
     (void)tmp;
     if (d != TC_D) return SED_ERR_UNSUPPORTED;
-    const bool has_lo = (prec_mode == 1);
+    const bool has_lo = (prec_mode == 1 || prec_mode == 3);
     const size_t elems = (size_t)B * N * TC_D;
     // fp16 operands: X (hi, lo) and two ping-pong Q buffers (hi, lo)
     ensure_pool_config();
@@ -323,7 +325,9 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
         const CUtensorMap& cqh = it == 0 ? mxh : mqh[(it - 1) & 1];
         const CUtensorMap& cql = it == 0 ? mxl : mql[(it - 1) & 1];
         TcParams p{bw, it == iterations - 1 ? out : nullptr, qh[it & 1], has_lo ? ql[it & 1] : nullptr, N, kernel_type};
-        rc = has_lo ? launch_tc<3, 2>(cqh, cql, mxh, mxl, p, B, st) : launch_tc<1, 1>(cqh, cql, mxh, mxl, p, B, st);
+        rc = prec_mode == 1   ? launch_tc<3, 2>(cqh, cql, mxh, mxl, p, B, st)
+             : prec_mode == 3 ? launch_tc<3, 1>(cqh, cql, mxh, mxl, p, B, st)
+                              : launch_tc<1, 1>(cqh, cql, mxh, mxl, p, B, st);
     }
     cudaFreeAsync(buf, st);
     return rc;

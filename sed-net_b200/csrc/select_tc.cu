@@ -410,53 +410,194 @@ select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_consta
 // Single-pass variant for k <= 64 (the kNN graph of the encoder): the Gram runs ONCE.  Each query row is owned by
 // one thread that keeps, in shared memory, a private candidate buffer of SS_CAP (score, index) entries and a
 // threshold register: a candidate is appended iff its score beats the threshold (predicated stores, no divergence).
-// When any buffer of the warp is about to overflow, every lane prunes its own buffer: a bisection over the
-// order-preserving integer image of the scores finds a pivot that keeps between k and k + SS_WIN entries, the buffer is
-// compacted in place (index order preserved, so ties keep going to the lowest index) and the pivot becomes the new
-// threshold.  A threshold only has to guarantee that >= k earlier candidates are at least as good, so the prune need
-// not be exact; the final prune (window 0) is, and the k survivors of a row are sorted by one warp.
-// Expected appends per row ~ k ln(N/k) (a few hundred of 10 000 candidates); ~6 prunes per row.
+// When any buffer of the warp is about to overflow, every lane prunes its own buffer: an interpolation / bisection
+// search over the order-preserving integer image of the scores finds a pivot that keeps between k and k + SS_WIN
+// entries, the buffer is compacted in place (index order preserved, so ties keep going to the lowest index) and the
+// pivot becomes the new threshold.  A threshold only has to guarantee that >= k earlier candidates are at least as
+// good, so the prune need not be exact; the final prune (window 0) is, and the k survivors of a row are sorted by one
+// warp.  Expected appends per row ~ k ln(N/k) (a few hundred of 10 000 candidates); ~6 prunes per row.
+// Candidate tiles are 64 wide (two 32-candidate chunks per thread), four TMEM buffers deep; padding candidates carry a
+// squared norm of +inf, so their score is -inf (or NaN) and never passes the threshold test.
 constexpr int SS_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 select (thread per row)
-constexpr int SS_CAP = 168;       // entries per row buffer
+constexpr int SS_NC = 64;         // candidates per tile
+constexpr int SS_CAP = 188;       // entries per row buffer (row-major; 752-B / 376-B row strides keep LDS.128 / LDS.64 conflict-free)
 constexpr int SS_WIN = 24;        // a prune leaves between k and k + SS_WIN entries
-constexpr int SS_STAGES = 2;
-struct SelTrue { static constexpr bool value = true; };
-struct SelFalse { static constexpr bool value = false; };
+constexpr int SS_STAGES = 3;
+constexpr int SS_NBUF = 4;        // TMEM buffers of 128 columns (two 64-column accumulators)
+constexpr int SS_XCRING = 8;      // candidate-norm slices in flight: >= SS_STAGES + SS_NBUF (producer's maximum lead)
+constexpr uint32_t SS_XPART = 64 * 128;                  // one candidate tile part: 64 rows x 64 channels fp16
+constexpr uint32_t SS_KEY_ROW = SS_CAP * 4, SS_IDX_ROW = SS_CAP * 2;
+constexpr uint32_t SS_KEY_BYTES = SS_KEY_ROW * 128, SS_IDX_BYTES = SS_IDX_ROW * 128;
+constexpr uint32_t SS_NEG_INF = 0xff800000u;
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("{ .reg .u16 t; ld.shared.u16 t, [%1]; cvt.u32.u16 %0, t; }" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t; }" ::"r"(a), "r"(v));
+}
+template <int NS>
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {   // producer-side wait: back off
+    uint32_t ok;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) break;
+        __nanosleep(NS);
+    }
+}
+
+__device__ __forceinline__ void lds_v4(uint32_t a, float (&v)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+}
+
+// number of entries of a row buffer (uniform bound cmax, a multiple of 4; padding entries are -inf) with
+// key >= pivot / key > pivot.  Rows are contiguous, so one LDS.128 brings four entries.
+template <bool STRICT>
+__device__ __forceinline__ int ss_count(uint32_t key_row, int cmax, float pivot) {
+    int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll 4
+    for (int i = 0; i < cmax; i += 4) {
+        float v[4];
+        lds_v4(key_row + (uint32_t)i * 4u, v);
+        c0 += (STRICT ? (v[0] > pivot) : (v[0] >= pivot)) ? 1 : 0;
+        c1 += (STRICT ? (v[1] > pivot) : (v[1] >= pivot)) ? 1 : 0;
+        c2 += (STRICT ? (v[2] > pivot) : (v[2] >= pivot)) ? 1 : 0;
+        c3 += (STRICT ? (v[3] > pivot) : (v[3] >= pivot)) ? 1 : 0;
+    }
+    return (c0 + c1) + (c2 + c3);
+}
+
+// Warp-wide prune of the 32 private buffers (all lanes call; lanes with cnt <= k + win keep everything).
+// On return every lane holds between k and k + win entries (exactly min(cnt, k) for win == 0), in index order,
+// slots >= cnt are -inf, and thr is a valid threshold (>= k kept entries are >= thr).
+__device__ __noinline__ void ss_prune(uint32_t key_row, uint32_t idx_row, int k, int win, int& cnt_io, float& thr_io) {
+    int cnt = cnt_io;
+    float thr = thr_io;
+    const int cmax = min((__reduce_max_sync(0xffffffffu, cnt) + 3) & ~3, SS_CAP);
+    const bool active = cnt > k + win;
+    float mx;
+    {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll 4
+        for (int i = 0; i < cmax; i += 4) {
+            float v[4];
+            lds_v4(key_row + (uint32_t)i * 4u, v);
+            m0 = fmaxf(m0, v[0]); m1 = fmaxf(m1, v[1]); m2 = fmaxf(m2, v[2]); m3 = fmaxf(m3, v[3]);
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+    }
+    float lo_f = thr;
+    if (!(thr > -INFINITY)) {   // first prune of the row: every entry so far was accepted; start from the minimum
+        float mn = INFINITY;
+        for (int i = 0; i < cnt; ++i) mn = fminf(mn, __uint_as_float(lds_u32(key_row + (uint32_t)i * 4u)));
+        lo_f = mn;
+    }
+    // invariant: count(>= lo) = c_lo >= k, count(>= hi) = c_hi < k (hi starts one step above the maximum)
+    uint32_t lo_u = f2ord(lo_f), hi_u = f2ord(mx) + 1u;
+    int c_lo = cnt, c_hi = 0;
+    const float target = (float)k + 0.5f * (float)win + 0.5f;
+    for (int it = 0; it < 80; ++it) {
+        const bool need = active && c_lo > k + win && hi_u - lo_u > 1u;
+        if (!__any_sync(0xffffffffu, need)) break;
+        uint32_t mid_u = lo_u + ((hi_u - lo_u) >> 1);
+        if (it < 3 || (it & 1)) {   // interpolate on the counts (the tail of the score distribution is near-linear)
+            const float lf = ord2f(lo_u), hf = ord2f(hi_u - 1u);
+            const float frac = ((float)c_lo - target) / (float)(c_lo - c_hi);
+            const uint32_t g_u = f2ord(fmaf(hf - lf, frac, lf));
+            if (need && g_u > lo_u && g_u < hi_u) mid_u = g_u;
+        }
+        const float mid_f = ord2f(mid_u);
+        const int c = ss_count<false>(key_row, cmax, mid_f);
+        if (need) {
+            if (c >= k) { lo_u = mid_u; lo_f = mid_f; c_lo = c; }
+            else { hi_u = mid_u; c_hi = c; }
+        }
+    }
+    // compaction: keep key > lo, and ties at lo in index order up to the quota (unlimited unless the search ended on a
+    // tie plateau wider than the window)
+    const bool plateau = active && c_lo > k + win;
+    int quota = 0x7fffffff;
+    if (__any_sync(0xffffffffu, plateau)) {
+        const int g = ss_count<true>(key_row, cmax, lo_f);
+        if (plateau) quota = max(k - g, 0);
+    }
+    if (active) {
+        int w = 0, t = 0;
+        const int cend = (cnt + 3) & ~3;
+        for (int r = 0; r < cend; r += 4) {
+            float v[4];
+            uint32_t i01, i23;
+            lds_v4(key_row + (uint32_t)r * 4u, v);
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(i01), "=r"(i23) : "r"(idx_row + (uint32_t)r * 2u));
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(key_row + (uint32_t)r * 4u), "r"(SS_NEG_INF));
+            const uint32_t iv[4] = {i01 & 0xffffu, i01 >> 16, i23 & 0xffffu, i23 >> 16};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool tie = (v[e] == lo_f);
+                const bool keep = (v[e] > lo_f) || (tie && t < quota);   // padding (-inf) never kept
+                t += tie ? 1 : 0;
+                if (keep) {
+                    sts_u32(key_row + (uint32_t)w * 4u, __float_as_uint(v[e]));
+                    sts_u16(idx_row + (uint32_t)w * 2u, iv[e]);
+                    ++w;
+                }
+            }
+        }
+        cnt = w;
+        thr = lo_f;
+    }
+    __syncwarp();
+    cnt_io = cnt;
+    thr_io = thr;
+}
 
 template <int MODE>
 __global__ void __launch_bounds__(SS_THREADS, 1)
 select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
                      const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, SelParams p) {
-    constexpr uint32_t PART_BYTES = BOX_BYTES;                     // 128 rows x 64 channels fp16
-    constexpr uint32_t TILE2 = 2 * PART_BYTES;                     // hi + lo
-    constexpr uint32_t KEY_BYTES = SS_CAP * 128 * 4, IDX_BYTES = SS_CAP * 128 * 2;
-    constexpr uint32_t BUF_COLS = 256;                             // two 128-column accumulators per TMEM buffer
+    constexpr uint32_t QPART = BOX_BYTES;                          // 128 rows x 64 channels fp16
+    constexpr uint32_t XSTAGE = 2 * SS_XPART;                      // hi + lo
+    constexpr uint32_t BUF_COLS = 128;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw0 = smem_u32(smem_raw);
     const uint32_t smem_base = (raw0 + 1023u) & ~1023u;
     const uint32_t q_addr = smem_base;
-    const uint32_t x_addr = q_addr + TILE2;
-    const uint32_t list_addr = x_addr + SS_STAGES * TILE2;
-    const uint32_t bar_base = list_addr + KEY_BYTES + IDX_BYTES;
+    const uint32_t x_addr = q_addr + 2 * QPART;
+    const uint32_t list_addr = x_addr + SS_STAGES * XSTAGE;
+    const uint32_t xc_addr = list_addr + SS_KEY_BYTES + SS_IDX_BYTES;       // [SS_XCRING][64] candidate squared norms
+    const uint32_t bar_base = xc_addr + SS_XCRING * SS_NC * 4;
     const uint32_t bar_q_full = bar_base;
     const uint32_t bar_x_full = bar_base + 8;
     const uint32_t bar_x_empty = bar_x_full + 8 * SS_STAGES;
-    const uint32_t bar_s_full = bar_x_empty + 8 * SS_STAGES;   // [2]
-    const uint32_t bar_s_empty = bar_s_full + 16;              // [2]
-    const uint32_t tmem_slot = bar_s_empty + 16;
+    const uint32_t bar_s_full = bar_x_empty + 8 * SS_STAGES;   // [SS_NBUF]
+    const uint32_t bar_s_empty = bar_s_full + 8 * SS_NBUF;     // [SS_NBUF]
+    const uint32_t tmem_slot = bar_s_empty + 8 * SS_NBUF;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw0));
-    uint8_t* list_ptr = smem_raw + (list_addr - raw0);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, q0 = blockIdx.x * ST_M;
     const int Nc = p.Nc;
-    const int T = (Nc + ST_NC - 1) / ST_NC;
+    const int T = (Nc + SS_NC - 1) / SS_NC;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_q_full, 1);
         for (int s = 0; s < SS_STAGES; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_empty + 8 * i, 128); }
+        for (int i = 0; i < SS_NBUF; ++i) { mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_empty + 8 * i, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -471,53 +612,58 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
     if (warp == 0) {
         // ============================================================ TMA producer
         if (lane == 0) {
-            mbar_expect_tx(bar_q_full, TILE2);
+            mbar_expect_tx(bar_q_full, 2 * QPART);
             tma_load_3d(q_addr, &map_qh, bar_q_full, 0, q0, b);
-            tma_load_3d(q_addr + PART_BYTES, &map_ql, bar_q_full, 0, q0, b);
+            tma_load_3d(q_addr + QPART, &map_ql, bar_q_full, 0, q0, b);
             for (int j = 0; j < T; ++j) {
                 const int s = j % SS_STAGES;
-                if (j >= SS_STAGES) mbar_wait(bar_x_empty + 8 * s, ((j / SS_STAGES) - 1) & 1);
-                const uint32_t dst = x_addr + s * TILE2, bar = bar_x_full + 8 * s;
-                mbar_expect_tx(bar, TILE2);
-                tma_load_3d(dst, &map_xh, bar, 0, j * ST_NC, b);
-                tma_load_3d(dst + PART_BYTES, &map_xl, bar, 0, j * ST_NC, b);
+                if (j >= SS_STAGES) mbar_wait_relaxed<256>(bar_x_empty + 8 * s, ((j / SS_STAGES) - 1) & 1);
+                const uint32_t dst = x_addr + s * XSTAGE, bar = bar_x_full + 8 * s;
+                mbar_expect_tx(bar, XSTAGE + SS_NC * 4);
+                tma_load_3d(dst, &map_xh, bar, 0, j * SS_NC, b);
+                tma_load_3d(dst + SS_XPART, &map_xl, bar, 0, j * SS_NC, b);
+                // the tile's squared norms ride on the same barrier; their ring slot outlives the operand stage
+                // (the MMA frees the stage, the selection threads read the norms up to SS_NBUF tiles later)
+                bulk_load(xc_addr + (uint32_t)(j % SS_XCRING) * (SS_NC * 4), p.xxc + (long long)b * p.npad + j * SS_NC,
+                          SS_NC * 4, bar);
             }
         }
     } else if (warp == 1) {
         // ============================================================ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t IDESC = make_idesc(0);
-            mbar_wait(bar_q_full, 0);
+            constexpr uint32_t IDESC = make_idesc_n(0, SS_NC);
+            mbar_wait_relaxed<32>(bar_q_full, 0);
             for (int j = 0; j < T; ++j) {
-                const int s = j % SS_STAGES;
-                mbar_wait(bar_x_full + 8 * s, (j / SS_STAGES) & 1);
-                if (j >= 2) mbar_wait(bar_s_empty + 8 * (j & 1), ((j >> 1) - 1) & 1);
+                const int s = j % SS_STAGES, buf = j % SS_NBUF;
+                mbar_wait_relaxed<32>(bar_x_full + 8 * s, (j / SS_STAGES) & 1);
+                if (j >= SS_NBUF) mbar_wait_relaxed<32>(bar_s_empty + 8 * buf, ((j / SS_NBUF) - 1) & 1);
                 tc_fence_after();
-                const uint32_t xs = x_addr + s * TILE2;
-                const uint32_t d = tmem + (uint32_t)(j & 1) * BUF_COLS;
+                const uint32_t xs = x_addr + s * XSTAGE;
+                const uint32_t d = tmem + (uint32_t)buf * BUF_COLS;
                 if (MODE == SEL_PN) {
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
+                        // channels [0,16): points (3 used), [16,32): normals (3 used): one K-step each
 #pragma unroll
                         for (int term = 0; term < 3; ++term) {
-                            const uint32_t qa = q_addr + ((term == 2) ? PART_BYTES : 0);   // Qh, Qh, Ql
-                            const uint32_t xb = xs + ((term == 1) ? PART_BYTES : 0);       // Xh, Xl, Xh
-                            umma_ss(d + a * 128, make_desc(qa + a * 32, 16), make_desc(xb + a * 32, 16), IDESC, term > 0);
+                            const uint32_t qa = q_addr + ((term == 2) ? QPART : 0);         // Qh, Qh, Ql
+                            const uint32_t xb = xs + ((term == 1) ? SS_XPART : 0);          // Xh, Xl, Xh
+                            umma_ss(d + a * 64, make_desc(qa + a * 32, 16), make_desc(xb + a * 32, 16), IDESC, term > 0);
                         }
                     }
                 } else {
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {
-                        const uint32_t qa = q_addr + ((term == 2) ? PART_BYTES : 0);
-                        const uint32_t xb = xs + ((term == 1) ? PART_BYTES : 0);
-                        const uint32_t dd = d + (term == 0 ? 0u : 128u);                   // hi.hi | cross terms
+                        const uint32_t qa = q_addr + ((term == 2) ? QPART : 0);
+                        const uint32_t xb = xs + ((term == 1) ? SS_XPART : 0);
+                        const uint32_t dd = d + (term == 0 ? 0u : 64u);                     // hi.hi | cross terms
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
                             umma_ss(dd, make_desc(qa + ks * 32, 16), make_desc(xb + ks * 32, 16), IDESC,
                                     (ks > 0 || term == 2) ? 1u : 0u);
                     }
                 }
-                tc_commit(bar_s_full + 8 * (j & 1));
+                tc_commit(bar_s_full + 8 * buf);
                 tc_commit(bar_x_empty + 8 * s);
             }
         }
@@ -531,61 +677,28 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
         const float sc = scale_from_maxabs(p.maxabs_c[b]);
         const float inv2 = 2.0f * ((1.0f / sq) * (1.0f / sc));          // power of two: products below are exact
         const float xq = p.xxq[(long long)b * p.npad + min(q, p.npad - 1)];
-        const float* xxc = p.xxc + (long long)b * p.npad;
         const float W = p.W;
         const int k = p.k;
-        uint32_t* lkey = reinterpret_cast<uint32_t*>(list_ptr) + row;                      // lkey[pos * 128]
-        uint16_t* lidx = reinterpret_cast<uint16_t*>(list_ptr + KEY_BYTES) + row;          // lidx[pos * 128]
+        const uint32_t key_addr = list_addr + (uint32_t)row * SS_KEY_ROW;                  // key[pos] at + pos * 4
+        const uint32_t idx_addr = list_addr + SS_KEY_BYTES + (uint32_t)row * SS_IDX_ROW;   // idx[pos] at + pos * 2
         float thr = -INFINITY;
         int cnt = 0;
+        for (int i = 0; i < SS_CAP; i += 4)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(key_addr + (uint32_t)i * 4u), "r"(SS_NEG_INF));
 
-        // keeps between k and k + win entries (exactly min(cnt, k) for win == 0); thr <- pivot
-        auto prune = [&](int win) {
-            const bool active = cnt > k + win;
-            float lo_f = thr;
-            if (active) {
-                float mx = -INFINITY, mn = INFINITY;
-                for (int i = 0; i < cnt; ++i) {
-                    const float v = __uint_as_float(lkey[i * 128]);
-                    mx = fmaxf(mx, v); mn = fminf(mn, v);
-                }
-                if (!(lo_f > -INFINITY)) lo_f = mn;
-                // invariant: count(>= lo) >= k, count(>= hi) < k (hi starts one step above the maximum)
-                uint32_t lo_u = f2ord(lo_f), hi_u = f2ord(mx) + 1u;
-                int c_lo = cnt;
-                while (c_lo > k + win && hi_u - lo_u > 1u) {
-                    const uint32_t mid_u = lo_u + ((hi_u - lo_u) >> 1);
-                    const float mid_f = ord2f(mid_u);
-                    int c = 0;
-                    for (int i = 0; i < cnt; ++i) c += (__uint_as_float(lkey[i * 128]) >= mid_f) ? 1 : 0;
-                    if (c >= k) { lo_u = mid_u; lo_f = mid_f; c_lo = c; }
-                    else hi_u = mid_u;
-                }
-                int g = 0;
-                for (int i = 0; i < cnt; ++i) g += (__uint_as_float(lkey[i * 128]) > lo_f) ? 1 : 0;
-                const int quota = max(k - g, 0);
-                int w = 0, t = 0;
-                for (int r = 0; r < cnt; ++r) {
-                    const uint32_t kv = lkey[r * 128];
-                    const uint16_t iv = lidx[r * 128];
-                    const float v = __uint_as_float(kv);
-                    const bool tie = (v == lo_f);
-                    const bool keep = (v > lo_f) || (tie && t < quota);
-                    t += tie ? 1 : 0;
-                    if (keep) { lkey[w * 128] = kv; lidx[w * 128] = iv; ++w; }
-                }
-                cnt = w;
-                thr = lo_f;
-            }
-            __syncwarp();
+        auto maybe_prune = [&]() {
+            if (__any_sync(0xffffffffu, cnt > SS_CAP - 32)) ss_prune(key_addr, idx_addr, k, SS_WIN, cnt, thr);
         };
-
-        // one 32-candidate chunk of this thread's row
-        auto process_t = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int cbase, int nv, auto tail) {
+        // one 32-candidate chunk of this thread's row: v0 / v1 = the two accumulators
+        auto process = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int cbase, uint32_t xc_slot) {
+            float xc[32];   // the chunk's candidate norms, all loads up front
+#pragma unroll
+            for (int i4 = 0; i4 < 8; ++i4)
+                asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                    : "=f"(xc[i4 * 4]), "=f"(xc[i4 * 4 + 1]), "=f"(xc[i4 * 4 + 2]), "=f"(xc[i4 * 4 + 3]) : "r"(xc_slot + i4 * 16));
 #pragma unroll
             for (int i4 = 0; i4 < 8; ++i4) {
-                const float4 xc4 = __ldg(reinterpret_cast<const float4*>(xxc + cbase + i4 * 4));
-                const float xcs[4] = {xc4.x, xc4.y, xc4.z, xc4.w};
+                const float xcs[4] = {xc[i4 * 4], xc[i4 * 4 + 1], xc[i4 * 4 + 2], xc[i4 * 4 + 3]};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int i = i4 * 4 + e;
@@ -600,66 +713,60 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
                         // src/PointNet.py:76-78: inner = -2 x.x' ; pd = (-xx_j - inner) - xx_i
                         s = __fsub_rn(fmaf(inv2, __fadd_rn(a0, a1), -xcs[e]), xq);
                     }
-                    const bool pass = decltype(tail)::value ? ((s > thr) && (i < nv)) : (s > thr);
-                    if (pass) {
-                        lkey[cnt * 128] = __float_as_uint(s);
-                        lidx[cnt * 128] = (uint16_t)(cbase + i);
+                    if (s > thr) {   // addresses from cnt in fresh registers: no write-after-read wait on the stores
+                        sts_u32(key_addr + (uint32_t)cnt * 4u, __float_as_uint(s));
+                        sts_u16(idx_addr + (uint32_t)cnt * 2u, (uint32_t)(cbase + i));
                         ++cnt;
                     }
                 }
             }
         };
-        auto process = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int cbase, int nv) {
-            if (nv >= 32) process_t(v0, v1, cbase, nv, SelFalse{});   // warp-uniform: every tile but the last
-            else process_t(v0, v1, cbase, nv, SelTrue{});
-        };
 
+        uint32_t a0[32], a1[32], b0[32], b1[32];
+        mbar_wait(bar_s_full, 0);
+        tc_fence_after();
+        tmem_ld32(tmem + lane_addr, a0);
+        tmem_ld32(tmem + lane_addr + 64, a1);
+#pragma unroll 1
         for (int j = 0; j < T; ++j) {
-            const uint32_t sb = tmem + lane_addr + (uint32_t)(j & 1) * BUF_COLS;
-            const int nvalid = Nc - j * ST_NC;                         // >= 128 except in the last tile
-            mbar_wait(bar_s_full + 8 * (j & 1), (j >> 1) & 1);
-            tc_fence_after();
-            uint32_t a0[32], a1[32], b0[32], b1[32];
-            tmem_ld32(sb, a0);
-            tmem_ld32(sb + 128, a1);
+            const int buf = j % SS_NBUF;
+            const uint32_t sb = tmem + lane_addr + (uint32_t)buf * BUF_COLS;
+            tmem_ld_wait();                         // chunk 0 of tile j has landed in (a0, a1)
+            tmem_ld32(sb + 32, b0);                 // chunk 1 loads while chunk 0 is processed
+            tmem_ld32(sb + 64 + 32, b1);
+            const uint32_t xcs = xc_addr + (uint32_t)(j % SS_XCRING) * (SS_NC * 4);
+            maybe_prune();
+            process(a0, a1, j * SS_NC, xcs);
             tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 4; c += 2) {
-                // chunk c from (a0, a1) while chunk c + 1 loads into (b0, b1), then the other way round
-                tmem_ld32(sb + (c + 1) * 32, b0);
-                tmem_ld32(sb + 128 + (c + 1) * 32, b1);
-                if (__any_sync(0xffffffffu, cnt > SS_CAP - 32)) prune(SS_WIN);
-                process(a0, a1, j * ST_NC + c * 32, nvalid - c * 32);
-                tmem_ld_wait();
-                if (c + 2 < 4) {
-                    tmem_ld32(sb + (c + 2) * 32, a0);
-                    tmem_ld32(sb + 128 + (c + 2) * 32, a1);
-                }
-                if (__any_sync(0xffffffffu, cnt > SS_CAP - 32)) prune(SS_WIN);
-                process(b0, b1, j * ST_NC + (c + 1) * 32, nvalid - (c + 1) * 32);
-                tmem_ld_wait();
+            if (j + 1 < T) {                        // chunk 0 of tile j + 1 loads while chunk 1 is processed
+                const int nb = (j + 1) % SS_NBUF;
+                mbar_wait(bar_s_full + 8 * nb, ((j + 1) / SS_NBUF) & 1);
+                tc_fence_after();
+                const uint32_t sn = tmem + lane_addr + (uint32_t)nb * BUF_COLS;
+                tmem_ld32(sn, a0);
+                tmem_ld32(sn + 64, a1);
             }
+            maybe_prune();
+            process(b0, b1, j * SS_NC + 32, xcs + 128);
             tc_fence_before();
-            mbar_arrive(bar_s_empty + 8 * (j & 1));
+            mbar_arrive(bar_s_empty + 8 * buf);    // every tcgen05.ld of tile j has completed (both waits above)
         }
 
         // ---- exact top-k of the survivors, then one warp sorts each of its 32 rows
-        prune(0);
+        ss_prune(key_addr, idx_addr, k, 0, cnt, thr);
         __syncwarp();
-        // per-row survivor counts (normally k) through shuffles: the sorter of row r asks lane r
         for (int r = 0; r < 32; ++r) {
             const int rr = quarter * 32 + r;
             const int qq = q0 + rr;
             const int rcnt = __shfl_sync(0xffffffffu, cnt, r);
             if (qq >= p.Nq) break;
-            const uint32_t* rk = reinterpret_cast<const uint32_t*>(list_ptr) + rr;
-            const uint16_t* ri = reinterpret_cast<const uint16_t*>(list_ptr + KEY_BYTES) + rr;
+            const uint32_t rk = list_addr + (uint32_t)rr * SS_KEY_ROW, ri = list_addr + SS_KEY_BYTES + (uint32_t)rr * SS_IDX_ROW;
             unsigned long long e[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int pos = lane + 32 * h;
-                e[h] = (pos < rcnt) ? (((unsigned long long)f2ord(__uint_as_float(rk[pos * 128])) << 32) |
-                                       (0xFFFFFFFFu - (uint32_t)ri[pos * 128]))
+                e[h] = (pos < rcnt) ? (((unsigned long long)f2ord(__uint_as_float(lds_u32(rk + (uint32_t)pos * 4u))) << 32) |
+                                       (0xFFFFFFFFu - lds_u16(ri + (uint32_t)pos * 2u)))
                                     : 0ull;
             }
 #pragma unroll
@@ -704,7 +811,8 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
 template <int MODE>
 static int launch_stream(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& xh, const CUtensorMap& xl,
                          const SelParams& p, int B, cudaStream_t st) {
-    constexpr size_t smem = (size_t)(SS_STAGES + 1) * 2 * BOX_BYTES + (size_t)SS_CAP * 128 * 6 + 1024 + 256;
+    constexpr size_t smem = (size_t)2 * BOX_BYTES + (size_t)SS_STAGES * 2 * SS_XPART + SS_KEY_BYTES + SS_IDX_BYTES +
+                            SS_XCRING * SS_NC * 4 + 1024 + 256;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     auto kern = select_stream_kernel<MODE>;
     SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -713,6 +821,7 @@ static int launch_stream(const CUtensorMap& qh, const CUtensorMap& ql, const CUt
     SED_CHECK_LAUNCH();
     return SED_OK;
 }
+
 
 // ---------------------------------------------------------------------------------------------- operand packing
 __global__ void maxabs_kernel(const float* __restrict__ x, long long bstride, long long n, float* __restrict__ out) {
@@ -733,7 +842,7 @@ __global__ void pack_cm_kernel(const float* __restrict__ x, long long bstride, i
                                float* __restrict__ xx) {
     const int b = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= npad) return;
-    if (n >= N) { xx[(long long)b * npad + n] = 0.f; return; }
+    if (n >= N) { xx[(long long)b * npad + n] = INFINITY; return; }   // padding: score -inf, never selected
     const float s = scale_from_maxabs(maxabs[b]);
     const float* xb = x + (long long)b * bstride + n;
     __half* ho = hi + ((long long)b * N + n) * 64;
@@ -822,11 +931,16 @@ int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn
         SelParams p{xx, xx, mx, mx, 1.0f, N, N, npad, k, nullptr, W, idx, idx64, nullptr};
         // SEDNET_B200_KNN=radix selects the multi-pass radix kernel (A/B comparisons); default: single-pass streaming
         static const bool radix = [] { const char* e = getenv("SEDNET_B200_KNN"); return e && !strcmp(e, "radix"); }();
-        if (rc == SED_OK && radix)
+        if (rc == SED_OK && (radix || (pn && !(W >= 0.f)))) {
             rc = pn ? launch_select<SEL_PN, OUT_IDX, 1, 8>(mh, ml, mh, ml, p, B, st)
                     : launch_select<SEL_L2, OUT_IDX, 1, 8>(mh, ml, mh, ml, p, B, st);
-        else if (rc == SED_OK)
-            rc = pn ? launch_stream<SEL_PN>(mh, ml, mh, ml, p, B, st) : launch_stream<SEL_L2>(mh, ml, mh, ml, p, B, st);
+        } else if (rc == SED_OK) {
+            CUtensorMap xh, xl;   // candidate tiles of the streaming kernel are 64 rows
+            rc = make_map_f16(&xh, hi, B, N, 64, SS_NC);
+            if (rc == SED_OK) rc = make_map_f16(&xl, lo, B, N, 64, SS_NC);
+            if (rc == SED_OK)
+                rc = pn ? launch_stream<SEL_PN>(mh, ml, xh, xl, p, B, st) : launch_stream<SEL_L2>(mh, ml, xh, xl, p, B, st);
+        }
     }
     cudaFreeAsync(buf, st);
     return rc;

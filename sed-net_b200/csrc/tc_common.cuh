@@ -40,6 +40,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// 1-D bulk copy global -> shared (bytes multiple of 16, both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -102,10 +108,11 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 // Instruction descriptor kind::f16: D = F32, A = B = F16, M = 128, N = 128; b_mn_major selects the B layout.
-__host__ __device__ constexpr uint32_t make_idesc(int b_mn_major) {
-    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | ((uint32_t)b_mn_major << 16) | ((128u >> 3) << 17) |
+__host__ __device__ constexpr uint32_t make_idesc_n(int b_mn_major, int n) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | ((uint32_t)b_mn_major << 16) | (((uint32_t)n >> 3) << 17) |
            ((128u >> 4) << 24);
 }
+__host__ __device__ constexpr uint32_t make_idesc(int b_mn_major) { return make_idesc_n(b_mn_major, 128); }
 
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -125,13 +132,13 @@ inline EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// (B, N, width) fp16 row-major, box 128 rows x 64 channels, 128B swizzle, out-of-range rows read as zero
-inline int make_map_f16(CUtensorMap* m, const __half* base, int B, int N, int width) {
+// (B, N, width) fp16 row-major, box box_rows x 64 channels, 128B swizzle, out-of-range rows read as zero
+inline int make_map_f16(CUtensorMap* m, const __half* base, int B, int N, int width, int box_rows = 128) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return SED_ERR_UNSUPPORTED;
     const cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)N, (cuuint64_t)B};
     const cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)N * width * 2};
-    const cuuint32_t box[3] = {64, 128, 1};
+    const cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

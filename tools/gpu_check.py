@@ -164,19 +164,19 @@ def stage_pipeline():
 
 def stage_tc():
     """tcgen05 mean-shift (prec 1 = split FP16, prec 2 = single FP16) against the FP32 FFMA kernel."""
-    for n, npatch, sigma in ((300, 2, 0.02), (2048, 9, 0.02), (10000, 14, 0.02)):
+    for n, npatch, sigma in ((2048, 9, 0.02), (10000, 14, 0.02), (10000, 14, 0.005), (10000, 30, 0.04)):
         _, _, lab, _, _ = synth.make_cloud(400 + n, n, n_patches=npatch, min_pts=100)
         X = t(synth.make_embedding(lab, 128, sigma, n)).to(dev)
         bw = torch.clamp(mean_shift.MeanShift(0).compute_bandwidth(X, 10000, 0.015), min=0.003) if n >= 150 else 0.3
         for iters in (1, 50):
             ref, t0 = timed(lambda: mean_shift.MeanShift(0).mean_shift_(X, bw, iters)[0], n=1)
-            for prec in (1, 2):
+            for prec in (1, 3, 2):
                 got, tm = timed(lambda: mean_shift.MeanShift(prec).mean_shift_(X, bw, iters)[0], n=1)
                 diff = (got - ref).abs().max().item()
                 nrm = (torch.linalg.norm(got, dim=1) - 1).abs().max().item()
                 print(f"tc N{n} iters{iters} prec{prec}: max|tc - ffma| {diff:.3e} norm err {nrm:.1e} bw {float(bw):.4f} "
                       f"nan {bool(torch.isnan(got).any())}  tc {tm:.2f} ms ffma {t0:.2f} ms")
-        for prec in (1, 2):
+        for prec in (1, 3, 2):
             newX, center, bw2, labels = mean_shift.MeanShift(prec).mean_shift(X, 10000, 0.015, 50)
             print(f"   prec{prec}: labels match planted partition {(canon(labels.cpu().numpy()) == canon(lab)).all()} "
                   f"n_centers {center.shape[0]}")
