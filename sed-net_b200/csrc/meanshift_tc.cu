@@ -31,6 +31,8 @@ constexpr int TILE_BYTES = 2 * BOX_BYTES;       // 128 rows x 128 fp16
 constexpr float kOperandScale = 8.0f;
 
 struct TcParams {
+    const __half* q_hi;     // (B,N,128) current positions (operand of this iteration), hi / lo parts
+    const __half* q_lo;
     const float* bw;        // (B)
     float* out_f32;         // (B,N,128) or null
     __half* q_next_hi;      // (B,N,128) operand of the next iteration
@@ -41,17 +43,15 @@ struct TcParams {
 // NS: MMAs per S tile (1 or 3); NV: MMAs per PV tile (1 or 2)
 template <int NS, int NV>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
-                   const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, TcParams p) {
+ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, TcParams p) {
     constexpr bool HAS_LO = (NS > 1) || (NV > 1);
-    constexpr int STAGES = HAS_LO ? 2 : 4;
+    constexpr int STAGES = HAS_LO ? 3 : 6;
     constexpr int PARTS = HAS_LO ? 2 : 1;
     constexpr uint32_t STAGE_BYTES = PARTS * TILE_BYTES;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // 128B swizzle needs 1024-B alignment
-    const uint32_t q_addr = smem_base;                                  // [hi | lo] x 32 KB
-    const uint32_t x_addr = q_addr + STAGE_BYTES;                       // STAGES x [hi | lo]
+    const uint32_t x_addr = smem_base;                                  // STAGES x [hi | lo] x 32 KB
     const uint32_t bar_base = x_addr + STAGES * STAGE_BYTES;
     // barriers (8 B each)
     const uint32_t bar_q_full = bar_base;
@@ -69,13 +69,13 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_cons
     const int T = (N + TC_NK - 1) / TC_NK;
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_q_full, 1);
+        mbar_init(bar_q_full, 256);
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_p_full + 8 * i, 128); }
         mbar_init(bar_o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {  // TMEM: S0 [0,128) S1 [128,256) O [256,384): allocate 512 columns (power of two)
+    if (warp == 2) {  // TMEM: S0 [0,128) S1 [128,256) O [256,384) Qhi [384,448) Qlo [448,512)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -87,13 +87,6 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_cons
     if (warp == 0) {
         // ============================================================ TMA producer
         if (lane == 0) {
-            mbar_expect_tx(bar_q_full, STAGE_BYTES);
-            tma_load_3d(q_addr, &map_qh, bar_q_full, 0, q0, b);
-            tma_load_3d(q_addr + BOX_BYTES, &map_qh, bar_q_full, 64, q0, b);
-            if (HAS_LO) {
-                tma_load_3d(q_addr + TILE_BYTES, &map_ql, bar_q_full, 0, q0, b);
-                tma_load_3d(q_addr + TILE_BYTES + BOX_BYTES, &map_ql, bar_q_full, 64, q0, b);
-            }
             for (int j = 0; j < T; ++j) {
                 const int s = j % STAGES;
                 if (j >= STAGES) mbar_wait(bar_x_empty + 8 * s, ((j / STAGES) - 1) & 1);
@@ -112,19 +105,22 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_cons
         if (lane == 0) {
             constexpr uint32_t IDESC_S = make_idesc(0), IDESC_PV = make_idesc(1);
             const uint32_t tmem_o = tmem + 256;
-            // S(j) = sum over terms (a_part, b_part) of Q[a_part] X[b_part]^T, K = 128 channels = 8 steps of 16
+            // S(j) = sum over terms (a_part, b_part) of Q[a_part] X[b_part]^T, K = 128 channels = 8 steps of 16.
+            // Q lives in TMEM for the whole CTA (A operand from TMEM: 8 columns of fp16 pairs per K-step), so the S
+            // phase reads only the X tile from shared memory -- with both operands in shared memory an M = N = 128
+            // MMA needs 128 B/clk, all the shared-memory bandwidth there is.
             auto issue_s = [&](int j) {
                 const uint32_t xs = x_addr + (j % STAGES) * STAGE_BYTES;
                 const uint32_t d = tmem + (uint32_t)(j & 1) * 128u;
                 uint32_t acc = 0;
 #pragma unroll
                 for (int term = 0; term < NS; ++term) {
-                    const uint32_t qa = q_addr + ((term == 2) ? TILE_BYTES : 0);   // Qh, Qh, Ql
+                    const uint32_t qa = tmem + 384u + ((term == 2) ? 64u : 0u);    // Qh, Qh, Ql
                     const uint32_t xb = xs + ((term == 1) ? TILE_BYTES : 0);       // Xh, Xl, Xh
 #pragma unroll
                     for (int ks = 0; ks < TC_D / 16; ++ks) {
                         const uint32_t off = (ks >> 2) * BOX_BYTES + (ks & 3) * 32;  // 4 K-steps per 128-B swizzle row
-                        umma_ss(d, make_desc(qa + off, 16), make_desc(xb + off, 16), IDESC_S, acc);
+                        umma_ts(d, qa + ks * 8, make_desc(xb + off, 16), IDESC_S, acc);
                         acc = 1;
                     }
                 }
@@ -175,6 +171,28 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_cons
         // epanechnikov: 0.75 * (1 - (2 - 2s)/b^2) = S_acc * e1 + e0
         const float e1 = 1.5f * inv_b2 / (kOperandScale * kOperandScale);
         const float e0 = 0.75f - 1.5f * inv_b2;
+        {   // ---- this thread's query row -> TMEM (group 0: hi part or channels 0-63, group 1: lo part or 64-127)
+            const int qrow = q0 + row;
+            const __half* src = (HAS_LO && group == 1) ? p.q_lo : p.q_hi;
+            const uint4* g4 = reinterpret_cast<const uint4*>(src + ((long long)b * N + min(qrow, N - 1)) * TC_D) +
+                              (HAS_LO ? 0 : group * 8);
+            const uint32_t qb = tmem + lane_addr + 384u + (HAS_LO ? (uint32_t)group * 64u : (uint32_t)group * 32u);
+            constexpr int NQ = HAS_LO ? 4 : 2;   // 16-column stores
+#pragma unroll
+            for (int c = 0; c < NQ; ++c) {
+                uint32_t w[16];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (qrow < N) v = __ldg(g4 + c * 4 + i);
+                    w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+                }
+                tmem_st16(qb + c * 16, w);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_q_full);
+        }
         for (int j = group; j < T; j += 2) {
             const uint32_t sb = tmem + lane_addr + (uint32_t)(j & 1) * 128u;
             mbar_wait(bar_s_full + 8 * (j & 1), (j >> 1) & 1);
@@ -219,7 +237,7 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_cons
 #pragma unroll
             for (int i = 0; i < 32; ++i) { const float o = __uint_as_float(v[i]); ss = fmaf(o, o, ss); }
         }
-        float* ssx = reinterpret_cast<float*>(smem_raw + (q_addr - smem_u32(smem_raw)));   // Q tile is dead by now
+        float* ssx = reinterpret_cast<float*>(smem_raw + (x_addr - smem_u32(smem_raw)));   // X stages are dead by now
         ssx[group * 128 + row] = ss;
         asm volatile("bar.sync 1, 256;" ::: "memory");
         const float rn = 1.0f / sqrtf(ssx[row] + ssx[128 + row]);
@@ -286,15 +304,14 @@ __global__ void split_f16_kernel(const float* __restrict__ x, long long n, __hal
 }
 
 template <int NS, int NV>
-static int launch_tc(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& xh, const CUtensorMap& xl,
-                     const TcParams& p, int B, cudaStream_t st) {
+static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const TcParams& p, int B, cudaStream_t st) {
     constexpr bool HAS_LO = (NS > 1) || (NV > 1);
-    constexpr int STAGES = HAS_LO ? 2 : 4;
-    constexpr size_t smem = (size_t)(STAGES + 1) * (HAS_LO ? 2 : 1) * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    constexpr int STAGES = HAS_LO ? 3 : 6;
+    constexpr size_t smem = (size_t)STAGES * (HAS_LO ? 2 : 1) * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     auto kern = ms_shift_tc_kernel<NS, NV>;
     SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((p.N + TC_M - 1) / TC_M, B);
-    kern<<<grid, TC_THREADS, smem, st>>>(qh, ql, xh, xl, p);
+    kern<<<grid, TC_THREADS, smem, st>>>(xh, xl, p);
     SED_CHECK_LAUNCH();
     return SED_OK;
 }
@@ -313,21 +330,18 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
            *ql[2] = {buf + 3 * elems, buf + 5 * elems};
     split_f16_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, st>>>(X, (long long)elems, xh, xl);
     ++g_sed_launches;
-    CUtensorMap mxh, mxl, mqh[2], mql[2];
+    CUtensorMap mxh, mxl;
     int rc = make_map_f16(&mxh, xh, B, N, TC_D);
     if (rc == SED_OK) rc = make_map_f16(&mxl, xl, B, N, TC_D);
-    for (int i = 0; i < 2 && rc == SED_OK; ++i) {
-        rc = make_map_f16(&mqh[i], qh[i], B, N, TC_D);
-        if (rc == SED_OK) rc = make_map_f16(&mql[i], ql[i], B, N, TC_D);
-    }
     for (int it = 0; it < iterations && rc == SED_OK; ++it) {
         // iteration 0 reads Q = X; iteration it > 0 reads ping-pong buffer (it-1)&1 and writes buffer it&1
-        const CUtensorMap& cqh = it == 0 ? mxh : mqh[(it - 1) & 1];
-        const CUtensorMap& cql = it == 0 ? mxl : mql[(it - 1) & 1];
-        TcParams p{bw, it == iterations - 1 ? out : nullptr, qh[it & 1], has_lo ? ql[it & 1] : nullptr, N, kernel_type};
-        rc = prec_mode == 1   ? launch_tc<3, 2>(cqh, cql, mxh, mxl, p, B, st)
-             : prec_mode == 3 ? launch_tc<3, 1>(cqh, cql, mxh, mxl, p, B, st)
-                              : launch_tc<1, 1>(cqh, cql, mxh, mxl, p, B, st);
+        const __half* cqh = it == 0 ? xh : qh[(it - 1) & 1];
+        const __half* cql = it == 0 ? xl : ql[(it - 1) & 1];
+        TcParams p{cqh, cql, bw, it == iterations - 1 ? out : nullptr, qh[it & 1], has_lo ? ql[it & 1] : nullptr, N,
+                   kernel_type};
+        rc = prec_mode == 1   ? launch_tc<3, 2>(mxh, mxl, p, B, st)
+             : prec_mode == 3 ? launch_tc<3, 1>(mxh, mxl, p, B, st)
+                              : launch_tc<1, 1>(mxh, mxl, p, B, st);
     }
     cudaFreeAsync(buf, st);
     return rc;
