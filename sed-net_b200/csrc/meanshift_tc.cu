@@ -19,6 +19,10 @@
 //     prec_mode 2:  S = Qh Xh,                               O = Ph Xh           (fast)
 // The scale 8 keeps hi/lo away from the bottom of the FP16 range; 64 = 8*8 is folded into the exp2 argument and
 // the factor 8 on O vanishes in the normalisation.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "tc_common.cuh"
 
 namespace sed {
@@ -38,6 +42,13 @@ struct TcParams {
     __half* q_next_hi;      // (B,N,128) operand of the next iteration
     __half* q_next_lo;      // or null when the mode has no lo part
     int N, kernel_type;
+    // work decomposition: CTAs [0, full_ctas) own one 128-row query tile over all keys; the remaining `rem` query
+    // tiles (the partial last wave) are each split over `parts` CTAs by key range, partial sums meet in `part_o`
+    // (rem, parts, 128, 128) f32 and the last CTA to arrive (part_cnt) normalises and writes the row.
+    int qt_per_cloud, full_ctas, parts, tiles_per_part;
+    float* part_o;
+    int* part_cnt;
+    int grid_ctas;
 };
 
 // NS: MMAs per S tile (1 or 3); NV: MMAs per PV tile (1 or 2)
@@ -64,9 +75,18 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = blockIdx.y, q0 = blockIdx.x * TC_M;
     const int N = p.N;
-    const int T = (N + TC_NK - 1) / TC_NK;
+    const int T_all = (N + TC_NK - 1) / TC_NK;
+    int tile_id = blockIdx.x, part = 0, t0 = 0, T = T_all;
+    const bool split = (int)blockIdx.x >= p.full_ctas;
+    if (split) {
+        const int r = blockIdx.x - p.full_ctas;
+        tile_id = p.full_ctas + r / p.parts;
+        part = r % p.parts;
+        t0 = part * p.tiles_per_part;
+        T = min(T_all, t0 + p.tiles_per_part) - t0;     // >= 1 by construction
+    }
+    const int b = tile_id / p.qt_per_cloud, q0 = (tile_id % p.qt_per_cloud) * TC_M;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_q_full, 256);
@@ -92,11 +112,11 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 if (j >= STAGES) mbar_wait(bar_x_empty + 8 * s, ((j / STAGES) - 1) & 1);
                 const uint32_t dst = x_addr + s * STAGE_BYTES, bar = bar_x_full + 8 * s;
                 mbar_expect_tx(bar, STAGE_BYTES);
-                tma_load_3d(dst, &map_xh, bar, 0, j * TC_NK, b);
-                tma_load_3d(dst + BOX_BYTES, &map_xh, bar, 64, j * TC_NK, b);
+                tma_load_3d(dst, &map_xh, bar, 0, (t0 + j) * TC_NK, b);
+                tma_load_3d(dst + BOX_BYTES, &map_xh, bar, 64, (t0 + j) * TC_NK, b);
                 if (HAS_LO) {
-                    tma_load_3d(dst + TILE_BYTES, &map_xl, bar, 0, j * TC_NK, b);
-                    tma_load_3d(dst + TILE_BYTES + BOX_BYTES, &map_xl, bar, 64, j * TC_NK, b);
+                    tma_load_3d(dst + TILE_BYTES, &map_xl, bar, 0, (t0 + j) * TC_NK, b);
+                    tma_load_3d(dst + TILE_BYTES + BOX_BYTES, &map_xl, bar, 64, (t0 + j) * TC_NK, b);
                 }
             }
         }
@@ -222,59 +242,108 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             tc_fence_before();
             mbar_arrive(bar_p_full + 8 * (j & 1));
         }
-        // ---- epilogue: new = O / ||O||  (thread = one full row of 128 channels)
+        // ---- epilogue: new = O / ||O||.  Thread (row, group) owns two of the row's four 32-channel chunks.
         mbar_wait(bar_o_full, 0);
         tc_fence_after();
         const uint32_t ob = tmem + lane_addr + 256u;
-        // each group owns two of the four 32-channel chunks; the squared norm is exchanged through shared memory
-        float ss = 0.f;
-#pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const int c = group * 2 + cc;
-            uint32_t v[32];
-            tmem_ld32(ob + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) { const float o = __uint_as_float(v[i]); ss = fmaf(o, o, ss); }
-        }
         float* ssx = reinterpret_cast<float*>(smem_raw + (x_addr - smem_u32(smem_raw)));   // X stages are dead by now
-        ssx[group * 128 + row] = ss;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float rn = 1.0f / sqrtf(ssx[row] + ssx[128 + row]);
-        const int q = q0 + row;
-        const long long rowoff = ((long long)b * N + q) * TC_D;
+        bool finish = true;
+        float* po = nullptr;
+        if (split) {
+            // partial sums of this key range -> part_o[slot][part][row][:]; the last part to arrive finishes the tile
+            const int slot = tile_id - p.full_ctas;
+            po = p.part_o + ((long long)slot * p.parts * TC_M + row) * TC_D;
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc) {
-            const int c = group * 2 + cc;
-            uint32_t v[32];
-            tmem_ld32(ob + c * 32, v);
-            tmem_ld_wait();
-            if (q < N) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = group * 2 + cc;
+                uint32_t v[32];
+                tmem_ld32(ob + c * 32, v);
+                tmem_ld_wait();
+                float4* dst = reinterpret_cast<float4*>(po + (long long)part * TC_M * TC_D + c * 32);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    __stcg(dst + i, make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3])));
+            }
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            int* flag = reinterpret_cast<int*>(ssx + 256);
+            if (warp == 2 && lane == 0) {
+                const int prev = atomicAdd(p.part_cnt + slot, 1);
+                const int last = (prev == p.parts - 1) ? 1 : 0;
+                if (last) p.part_cnt[slot] = 0;      // ready for the next iteration (stream-ordered launches)
+                *flag = last;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            finish = (*flag != 0);
+            if (finish) __threadfence();
+        }
+        if (finish) {
+            // chunk c of this thread's row: TMEM accumulator, or the fixed-order sum of the parts
+            auto get_chunk = [&](int c, float (&z)[32]) {
+                if (!split) {
+                    uint32_t v[32];
+                    tmem_ld32(ob + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(v[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) z[i] = 0.f;
+                    for (int pp = 0; pp < p.parts; ++pp) {
+                        const float4* src = reinterpret_cast<const float4*>(po + (long long)pp * TC_M * TC_D + c * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 t = __ldcg(src + i);
+                            z[4 * i] += t.x; z[4 * i + 1] += t.y; z[4 * i + 2] += t.z; z[4 * i + 3] += t.w;
+                        }
+                    }
+                }
+            };
+            float ss = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
                 float z[32];
+                get_chunk(group * 2 + cc, z);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) z[i] = __uint_as_float(v[i]) * rn;
-                if (p.out_f32) {
-                    float4* dst = reinterpret_cast<float4*>(p.out_f32 + rowoff + c * 32);
+                for (int i = 0; i < 32; ++i) ss = fmaf(z[i], z[i], ss);
+            }
+            ssx[group * 128 + row] = ss;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float rn = 1.0f / sqrtf(ssx[row] + ssx[128 + row]);
+            const int q = q0 + row;
+            const long long rowoff = ((long long)b * N + q) * TC_D;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) dst[i] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
-                }
-                uint32_t hi[16], lo[16];
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = group * 2 + cc;
+                float z[32];
+                get_chunk(c, z);
+                if (q < N) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float a0 = z[2 * i] * kOperandScale, a1 = z[2 * i + 1] * kOperandScale;
-                    const __half2 h = __floats2half2_rn(a0, a1);
-                    const float2 hf = __half22float2(h);
-                    const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
-                    hi[i] = *reinterpret_cast<const uint32_t*>(&h);
-                    lo[i] = *reinterpret_cast<const uint32_t*>(&l);
-                }
-                uint4* dh = reinterpret_cast<uint4*>(p.q_next_hi + rowoff + c * 32);
+                    for (int i = 0; i < 32; ++i) z[i] *= rn;
+                    if (p.out_f32) {
+                        float4* dst = reinterpret_cast<float4*>(p.out_f32 + rowoff + c * 32);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                if (HAS_LO && p.q_next_lo) {
-                    uint4* dl = reinterpret_cast<uint4*>(p.q_next_lo + rowoff + c * 32);
+                        for (int i = 0; i < 8; ++i) dst[i] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+                    }
+                    uint32_t hi[16], lo[16];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                    for (int i = 0; i < 16; ++i) {
+                        const float a0 = z[2 * i] * kOperandScale, a1 = z[2 * i + 1] * kOperandScale;
+                        const __half2 h = __floats2half2_rn(a0, a1);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(a0 - hf.x, a1 - hf.y);
+                        hi[i] = *reinterpret_cast<const uint32_t*>(&h);
+                        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                    uint4* dh = reinterpret_cast<uint4*>(p.q_next_hi + rowoff + c * 32);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                    if (HAS_LO && p.q_next_lo) {
+                        uint4* dl = reinterpret_cast<uint4*>(p.q_next_lo + rowoff + c * 32);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) dl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+                    }
                 }
             }
         }
@@ -310,8 +379,8 @@ static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const TcParam
     constexpr size_t smem = (size_t)STAGES * (HAS_LO ? 2 : 1) * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     auto kern = ms_shift_tc_kernel<NS, NV>;
     SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((p.N + TC_M - 1) / TC_M, B);
-    kern<<<grid, TC_THREADS, smem, st>>>(xh, xl, p);
+    (void)B;
+    kern<<<p.grid_ctas, TC_THREADS, smem, st>>>(xh, xl, p);
     SED_CHECK_LAUNCH();
     return SED_OK;
 }
@@ -322,10 +391,22 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
     if (d != TC_D) return SED_ERR_UNSUPPORTED;
     const bool has_lo = (prec_mode == 1 || prec_mode == 3);
     const size_t elems = (size_t)B * N * TC_D;
+    // one CTA per SM: whole waves of query tiles, then the partial wave split by key range over the idle SMs
+    const int qtc = (N + TC_M - 1) / TC_M, QT = B * qtc, T_all = (N + TC_NK - 1) / TC_NK;
+    int full = QT / kNumSMs * kNumSMs, rem = QT - full, parts = 1;
+    if (rem > 0) parts = std::min(std::min(kNumSMs / rem, 8), std::max(T_all / 8, 1));   // >= 8 key tiles per part
+    static const bool nosplit = getenv("SEDNET_B200_MS_NOSPLIT") != nullptr;   // A/B timing switch
+    if (parts <= 1 || nosplit) { full = QT; rem = 0; parts = 1; }
+    const int tpp = (T_all + parts - 1) / parts;
+    while (parts > 1 && (parts - 1) * tpp >= T_all) --parts;   // no empty part
+    const size_t part_bytes = (size_t)rem * parts * TC_M * TC_D * sizeof(float);
     // fp16 operands: X (hi, lo) and two ping-pong Q buffers (hi, lo)
     ensure_pool_config();
     __half* buf = nullptr;
-    SED_CUDA(cudaMallocAsync((void**)&buf, elems * sizeof(__half) * 6, st));
+    SED_CUDA(cudaMallocAsync((void**)&buf, elems * sizeof(__half) * 6 + part_bytes + (size_t)(rem + 1) * sizeof(int), st));
+    float* part_o = reinterpret_cast<float*>(buf + 6 * elems);
+    int* part_cnt = reinterpret_cast<int*>(reinterpret_cast<char*>(part_o) + part_bytes);
+    if (cudaMemsetAsync(part_cnt, 0, (size_t)(rem + 1) * sizeof(int), st) != cudaSuccess) { cudaFreeAsync(buf, st); return SED_ERR_CUDA_BASE - 1; }
     __half *xh = buf, *xl = buf + elems, *qh[2] = {buf + 2 * elems, buf + 4 * elems},
            *ql[2] = {buf + 3 * elems, buf + 5 * elems};
     split_f16_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, st>>>(X, (long long)elems, xh, xl);
@@ -338,7 +419,7 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
         const __half* cqh = it == 0 ? xh : qh[(it - 1) & 1];
         const __half* cql = it == 0 ? xl : ql[(it - 1) & 1];
         TcParams p{cqh, cql, bw, it == iterations - 1 ? out : nullptr, qh[it & 1], has_lo ? ql[it & 1] : nullptr, N,
-                   kernel_type};
+                   kernel_type, qtc, full, parts, tpp, part_o, part_cnt, full + rem * parts};
         rc = prec_mode == 1   ? launch_tc<3, 2>(mxh, mxl, p, B, st)
              : prec_mode == 3 ? launch_tc<3, 1>(mxh, mxl, p, B, st)
                               : launch_tc<1, 1>(mxh, mxl, p, B, st);

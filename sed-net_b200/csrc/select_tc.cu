@@ -484,10 +484,11 @@ __device__ __forceinline__ int ss_count(uint32_t key_row, int cmax, float pivot)
 // Warp-wide prune of the 32 private buffers (all lanes call; lanes with cnt <= k + win keep everything).
 // On return every lane holds between k and k + win entries (exactly min(cnt, k) for win == 0), in index order,
 // slots >= cnt are -inf, and thr is a valid threshold (>= k kept entries are >= thr).
-__device__ __noinline__ void ss_prune(uint32_t key_row, uint32_t idx_row, int k, int win, int& cnt_io, float& thr_io) {
+template <bool HAS_IDX>
+__device__ __noinline__ void ss_prune(uint32_t key_row, uint32_t idx_row, int cap, int k, int win, int& cnt_io, float& thr_io) {
     int cnt = cnt_io;
     float thr = thr_io;
-    const int cmax = min((__reduce_max_sync(0xffffffffu, cnt) + 3) & ~3, SS_CAP);
+    const int cmax = min((__reduce_max_sync(0xffffffffu, cnt) + 3) & ~3, cap);
     const bool active = cnt > k + win;
     float mx;
     {
@@ -540,9 +541,10 @@ __device__ __noinline__ void ss_prune(uint32_t key_row, uint32_t idx_row, int k,
         const int cend = (cnt + 3) & ~3;
         for (int r = 0; r < cend; r += 4) {
             float v[4];
-            uint32_t i01, i23;
+            uint32_t i01 = 0, i23 = 0;
             lds_v4(key_row + (uint32_t)r * 4u, v);
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(i01), "=r"(i23) : "r"(idx_row + (uint32_t)r * 2u));
+            if (HAS_IDX)
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(i01), "=r"(i23) : "r"(idx_row + (uint32_t)r * 2u));
             asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(key_row + (uint32_t)r * 4u), "r"(SS_NEG_INF));
             const uint32_t iv[4] = {i01 & 0xffffu, i01 >> 16, i23 & 0xffffu, i23 >> 16};
 #pragma unroll
@@ -552,7 +554,7 @@ __device__ __noinline__ void ss_prune(uint32_t key_row, uint32_t idx_row, int k,
                 t += tie ? 1 : 0;
                 if (keep) {
                     sts_u32(key_row + (uint32_t)w * 4u, __float_as_uint(v[e]));
-                    sts_u16(idx_row + (uint32_t)w * 2u, iv[e]);
+                    if (HAS_IDX) sts_u16(idx_row + (uint32_t)w * 2u, iv[e]);
                     ++w;
                 }
             }
@@ -687,7 +689,7 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
             asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(key_addr + (uint32_t)i * 4u), "r"(SS_NEG_INF));
 
         auto maybe_prune = [&]() {
-            if (__any_sync(0xffffffffu, cnt > SS_CAP - 32)) ss_prune(key_addr, idx_addr, k, SS_WIN, cnt, thr);
+            if (__any_sync(0xffffffffu, cnt > SS_CAP - 32)) ss_prune<true>(key_addr, idx_addr, SS_CAP, k, SS_WIN, cnt, thr);
         };
         // one 32-candidate chunk of this thread's row: v0 / v1 = the two accumulators
         auto process = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int cbase, uint32_t xc_slot) {
@@ -753,7 +755,7 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
         }
 
         // ---- exact top-k of the survivors, then one warp sorts each of its 32 rows
-        ss_prune(key_addr, idx_addr, k, 0, cnt, thr);
+        ss_prune<true>(key_addr, idx_addr, SS_CAP, k, 0, cnt, thr);
         __syncwarp();
         for (int r = 0; r < 32; ++r) {
             const int rr = quarter * 32 + r;
@@ -822,6 +824,203 @@ static int launch_stream(const CUtensorMap& qh, const CUtensorMap& ql, const CUt
     return SED_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------- streaming K-th score
+// compute_bandwidth (src/mean_shift.py:130-135): the K-th largest cosine score (= K-th smallest distance) of every
+// row, K up to KS_KMAX.  Same single-pass scheme as the kNN kernel above, for 128-channel rows: the query tile (hi and
+// lo parts) lives in TMEM for the whole CTA (A operand from TMEM), which leaves shared memory to three 32 KB candidate
+// stages and 252-entry row buffers; only the scores are kept (no indices).
+constexpr int KS_CAP = 252;       // 1008-B row stride: LDS.128 conflict-free
+constexpr int KS_KMAX = 200;
+constexpr int KS_WIN = 12;
+constexpr int KS_STAGES = 3;
+constexpr int KS_NBUF = 3;        // TMEM: 3 x 128 accumulator columns + 128 columns of Q
+constexpr uint32_t KS_XPART = 2 * SS_XPART;              // 64 rows x 128 channels fp16 (two 64-channel boxes)
+
+__global__ void __launch_bounds__(SS_THREADS, 1)
+kth_stream_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                  const __half* __restrict__ qh, const __half* __restrict__ ql, SelParams p) {
+    constexpr uint32_t XSTAGE = 2 * KS_XPART;
+    constexpr uint32_t BUF_COLS = 128;
+    constexpr uint32_t KEY_ROW = KS_CAP * 4;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw0 = smem_u32(smem_raw);
+    const uint32_t smem_base = (raw0 + 1023u) & ~1023u;
+    const uint32_t x_addr = smem_base;
+    const uint32_t list_addr = x_addr + KS_STAGES * XSTAGE;
+    const uint32_t bar_base = list_addr + KEY_ROW * 128;
+    const uint32_t bar_q_full = bar_base;
+    const uint32_t bar_x_full = bar_base + 8;
+    const uint32_t bar_x_empty = bar_x_full + 8 * KS_STAGES;
+    const uint32_t bar_s_full = bar_x_empty + 8 * KS_STAGES;   // [KS_NBUF]
+    const uint32_t bar_s_empty = bar_s_full + 8 * KS_NBUF;     // [KS_NBUF]
+    const uint32_t tmem_slot = bar_s_empty + 8 * KS_NBUF;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw0));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = blockIdx.y, q0 = blockIdx.x * ST_M;
+    const int Nc = p.Nc;
+    const int T = (Nc + SS_NC - 1) / SS_NC;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_q_full, 128);
+        for (int s = 0; s < KS_STAGES; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
+        for (int i = 0; i < KS_NBUF; ++i) { mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_empty + 8 * i, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ============================================================ TMA producer
+        if (lane == 0) {
+            for (int j = 0; j < T; ++j) {
+                const int s = j % KS_STAGES;
+                if (j >= KS_STAGES) mbar_wait_relaxed<256>(bar_x_empty + 8 * s, ((j / KS_STAGES) - 1) & 1);
+                const uint32_t dst = x_addr + s * XSTAGE, bar = bar_x_full + 8 * s;
+                mbar_expect_tx(bar, XSTAGE);
+                tma_load_3d(dst, &map_xh, bar, 0, j * SS_NC, b);
+                tma_load_3d(dst + SS_XPART, &map_xh, bar, 64, j * SS_NC, b);
+                tma_load_3d(dst + KS_XPART, &map_xl, bar, 0, j * SS_NC, b);
+                tma_load_3d(dst + KS_XPART + SS_XPART, &map_xl, bar, 64, j * SS_NC, b);
+            }
+        }
+    } else if (warp == 1) {
+        // ============================================================ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t IDESC = make_idesc_n(0, SS_NC);
+            mbar_wait_relaxed<32>(bar_q_full, 0);
+            for (int j = 0; j < T; ++j) {
+                const int s = j % KS_STAGES, buf = j % KS_NBUF;
+                mbar_wait_relaxed<32>(bar_x_full + 8 * s, (j / KS_STAGES) & 1);
+                if (j >= KS_NBUF) mbar_wait_relaxed<32>(bar_s_empty + 8 * buf, ((j / KS_NBUF) - 1) & 1);
+                tc_fence_after();
+                const uint32_t xs = x_addr + s * XSTAGE;
+                const uint32_t d = tmem + (uint32_t)buf * BUF_COLS;
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t qa = tmem + 384u + ((term == 2) ? 64u : 0u);         // Qh, Qh, Ql   (TMEM)
+                    const uint32_t xb = xs + ((term == 1) ? KS_XPART : 0);              // Xh, Xl, Xh
+                    const uint32_t dd = d + (term == 0 ? 0u : 64u);                     // hi.hi | cross terms
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_ts(dd, qa + ks * 8, make_desc(xb + (ks >> 2) * SS_XPART + (ks & 3) * 32, 16), IDESC,
+                                (ks > 0 || term == 2) ? 1u : 0u);
+                }
+                tc_commit(bar_s_full + 8 * buf);
+                tc_commit(bar_x_empty + 8 * s);
+            }
+        }
+    } else {
+        // ============================================================ selection: one thread per query row
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const int q = q0 + row;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        {   // this thread's query row -> TMEM columns [384,448) (hi) and [448,512) (lo)
+            const long long ro = ((long long)b * p.Nq + min(q, p.Nq - 1)) * 128;
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const uint4* g4 = reinterpret_cast<const uint4*>((part ? ql : qh) + ro);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (q < p.Nq) v = __ldg(g4 + c * 4 + i);
+                        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+                    }
+                    tmem_st16(tmem + lane_addr + 384u + part * 64u + c * 16u, w);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_q_full);
+        }
+        const float inv2 = 2.0f / (p.fixed_scale * p.fixed_scale);       // power of two
+        const int k = p.k;
+        const uint32_t key_addr = list_addr + (uint32_t)row * KEY_ROW;
+        float thr = -INFINITY;
+        int cnt = 0;
+        for (int i = 0; i < KS_CAP; i += 4)
+            asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(key_addr + (uint32_t)i * 4u), "r"(SS_NEG_INF));
+
+        auto maybe_prune = [&]() {
+            if (__any_sync(0xffffffffu, cnt > KS_CAP - 32)) ss_prune<false>(key_addr, 0u, KS_CAP, k, KS_WIN, cnt, thr);
+        };
+        // src/mean_shift.py:130: dist = 2 - 2 x.y ; score = -dist.  nv: valid candidates of the chunk (tail masking)
+        auto process = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int nv) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float s = fmaf(inv2, __fadd_rn(__uint_as_float(v0[i]), __uint_as_float(v1[i])), -2.0f);
+                if ((s > thr) && (i < nv)) {
+                    sts_u32(key_addr + (uint32_t)cnt * 4u, __float_as_uint(s));
+                    ++cnt;
+                }
+            }
+        };
+
+        uint32_t a0[32], a1[32], b0[32], b1[32];
+        mbar_wait(bar_s_full, 0);
+        tc_fence_after();
+        tmem_ld32(tmem + lane_addr, a0);
+        tmem_ld32(tmem + lane_addr + 64, a1);
+#pragma unroll 1
+        for (int j = 0; j < T; ++j) {
+            const int buf = j % KS_NBUF;
+            const uint32_t sb = tmem + lane_addr + (uint32_t)buf * BUF_COLS;
+            const int nvalid = Nc - j * SS_NC;
+            tmem_ld_wait();
+            tmem_ld32(sb + 32, b0);
+            tmem_ld32(sb + 64 + 32, b1);
+            maybe_prune();
+            process(a0, a1, nvalid);
+            tmem_ld_wait();
+            if (j + 1 < T) {
+                const int nb = (j + 1) % KS_NBUF;
+                mbar_wait(bar_s_full + 8 * nb, ((j + 1) / KS_NBUF) & 1);
+                tc_fence_after();
+                const uint32_t sn = tmem + lane_addr + (uint32_t)nb * BUF_COLS;
+                tmem_ld32(sn, a0);
+                tmem_ld32(sn + 64, a1);
+            }
+            maybe_prune();
+            process(b0, b1, nvalid - 32);
+            tc_fence_before();
+            mbar_arrive(bar_s_empty + 8 * buf);
+        }
+        // ---- exact K-th: prune to exactly K entries, their minimum is the answer
+        ss_prune<false>(key_addr, 0u, KS_CAP, k, 0, cnt, thr);
+        float mn = INFINITY;
+        for (int i = 0; i < cnt; ++i) mn = fminf(mn, __uint_as_float(lds_u32(key_addr + (uint32_t)i * 4u)));
+        if (q < p.Nq) p.out_kth[(long long)b * p.Nq + q] = mn;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+static int launch_kth_stream(const CUtensorMap& xh, const CUtensorMap& xl, const __half* qh, const __half* ql,
+                             const SelParams& p, int B, cudaStream_t st) {
+    constexpr size_t smem = (size_t)KS_STAGES * 2 * KS_XPART + (size_t)KS_CAP * 4 * 128 + 1024 + 256;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    SED_CUDA(cudaFuncSetAttribute(kth_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((p.Nq + ST_M - 1) / ST_M, B);
+    kth_stream_kernel<<<grid, SS_THREADS, smem, st>>>(xh, xl, qh, ql, p);
+    SED_CHECK_LAUNCH();
+    return SED_OK;
+}
 
 // ---------------------------------------------------------------------------------------------- operand packing
 __global__ void maxabs_kernel(const float* __restrict__ x, long long bstride, long long n, float* __restrict__ out) {
@@ -973,9 +1172,16 @@ int cos_select_tc(const float* Q, const float* Cand, int B, int Nq, int Nc, cons
     if (rc == SED_OK) rc = make_map_f16(&mch, ch, B, Nc, 128);
     if (rc == SED_OK) rc = make_map_f16(&mcl, cl, B, Nc, 128);
     SelParams p{nullptr, nullptr, nullptr, nullptr, scale, Nq, Nc, 0, K, nc_ptr, 0.f, idx_out, idx64, kth_out};
-    if (rc == SED_OK)
+    static const bool radix = [] { const char* e = getenv("SEDNET_B200_KNN"); return e && !strcmp(e, "radix"); }();
+    if (rc == SED_OK && kth_out && K <= KS_KMAX && !radix) {
+        CUtensorMap xh64, xl64;   // 64-row candidate tiles
+        rc = make_map_f16(&xh64, ch, B, Nc, 128, SS_NC);
+        if (rc == SED_OK) rc = make_map_f16(&xl64, cl, B, Nc, 128, SS_NC);
+        if (rc == SED_OK) rc = launch_kth_stream(xh64, xl64, qh, ql, p, B, st);
+    } else if (rc == SED_OK) {
         rc = kth_out ? launch_select<SEL_COS, OUT_KTH, 2, 7>(mqh, mql, mch, mcl, p, B, st)
                      : launch_select<SEL_COS, OUT_TOP1, 2, 8>(mqh, mql, mch, mcl, p, B, st);
+    }
     cudaFreeAsync(buf, st);
     return rc;
 }
