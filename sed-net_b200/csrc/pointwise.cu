@@ -8,6 +8,9 @@
 //                  k neighbours plus the GroupNorm sums.  GroupNorm-affine + LeakyReLU is monotone per channel,
 //                  so max_k f(y) = f(max_k y) or f(min_k y) depending on the sign of gamma*rstd;
 //   * gn_finalize / edge_finalize / pool_finalize / gemv_bias / head_combine / log_softmax: the small glue.
+#include <stdlib.h>
+#include <string.h>
+
 #include "internal.h"
 
 namespace sed {
@@ -424,6 +427,13 @@ int pw_gemm(const float* X, long long x_bstride, int ldx, const float* Wt, int l
             int ldy, int y_point_major, double* stats, float* mm, int B, int Cin, int Cout, int N, cudaStream_t stream) {
     if (!X || !Wt || B <= 0 || Cin <= 0 || Cout <= 0 || N <= 0) return SED_ERR_ARG;
     if ((in_a == nullptr) != (in_s == nullptr)) return SED_ERR_ARG;
+    // SEDNET_B200_PW=ffma forces the CUDA-core kernel of this file (A/B comparisons); default: tensor cores
+    static const bool ffma = [] { const char* e = getenv("SEDNET_B200_PW"); return e && !strcmp(e, "ffma"); }();
+    if (!ffma) {
+        const int rc = pw_gemm_tc(X, x_bstride, ldx, Wt, ldw, bias, bias_bstride, in_a, in_s, in_act, Y, y_bstride, ldy,
+                                  y_point_major, stats, mm, B, Cin, Cout, N, stream);
+        if (rc != SED_ERR_UNSUPPORTED) return rc;
+    }
     PwParams p{X, x_bstride, ldx, Wt, ldw, bias, bias_bstride, in_a, in_s, in_act, Y, y_bstride, ldy, y_point_major,
                stats, mm, Cin, Cout, N};
     dim3 grid((N + PW_BN - 1) / PW_BN, (Cout + PW_BM - 1) / PW_BM, B);

@@ -1,0 +1,369 @@
+// 1x1 convolutions of the SEDNet forward on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Same contract as pw_gemm (pointwise.cu):  Y = W . act(in_a * X + in_s) + bias  over channel-major activations, with the
+// GroupNorm partial statistics and the max/min pooling of the output produced in the epilogue -- reference
+// src/SEDNet.py:78-98 (EdgeConv per-point GEMM, mlp1) and :292-342 (conv1, conv2 and the heads).
+//
+// A CTA owns 128 points x up to 256 output channels:  D[point, co] (TMEM, FP32) = A[point, c] . B[co, c]^T
+//   * A = activations.  They are FP32 channel-major in HBM and need the previous layer's GroupNorm affine + activation,
+//     so eight producer warps load them coalesced, transform them, split each value into FP16 hi + lo and write the
+//     tcgen05 canonical MN-major / 128B-swizzle image (points contiguous) into shared memory themselves;
+//   * B = weights, pre-split per output row into FP16 hi + lo of w * 2^k (k per row: max|w| -> [1024, 2048)), K-major,
+//     fetched by TMA;  2^-k and the bias are applied in the epilogue;
+//   * D += Ah.Bh + Ah.Bl + Al.Bh : 22 significant bits per operand, FP32 accumulation;
+//   * epilogue: thread = point (TMEM lane), 32 output channels at a time: bias, statistics (sum / sum of squares per
+//     32-channel block, FP64 partials), max / min over the tile's points (recursive-halving shuffles), coalesced stores.
+#include "tc_common.cuh"
+
+namespace sed {
+
+constexpr int PT_THREADS = 320;          // warp 0 TMA (weights), warp 1 MMA, warps 2-9 producers + epilogue
+constexpr int PT_M = 128;                // points per CTA
+constexpr int PT_N = 256;                // output channels per CTA
+constexpr int PT_KC = 64;                // input channels per stage
+constexpr int PT_STAGES = 2;
+constexpr uint32_t PT_A_PART = PT_M * PT_KC * 2;     // 16 KB: [2 halves of 64 points][64 channels][64 points] fp16
+constexpr uint32_t PT_B_PART = PT_N * PT_KC * 2;     // 32 KB: [256 output rows][64 channels] fp16
+constexpr uint32_t PT_STAGE = 2 * PT_A_PART + 2 * PT_B_PART;   // hi + lo of both: 96 KB
+
+struct PtParams {
+    const float* X; long long x_bstride; int ldx;
+    const float* rscale;                       // (Cout) 2^-k of the weight rows
+    const float* bias; long long bias_bstride;
+    const float* in_a; const float* in_s; int in_act;
+    float* Y; long long y_bstride; int ldy; int y_point_major;
+    double* stats; float* mm;
+    int Cin, Cout, N;
+};
+
+// D = F32, A = B = F16, A MN-major (points contiguous), B K-major, M = 128
+__host__ __device__ constexpr uint32_t pt_idesc(int n) {
+    return (1u << 4) | (1u << 15) | (0u << 16) | (((uint32_t)n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ float pt_act(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v >= 0.f ? v : 0.2f * v;
+    return v;
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 1)
+pw_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__ CUtensorMap map_wl, PtParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw0 = smem_u32(smem_raw);
+    const uint32_t smem_base = (raw0 + 1023u) & ~1023u;
+    const uint32_t stage_addr = smem_base;                                  // PT_STAGES x [Ah | Al | Bh | Bl]
+    const uint32_t red_addr = stage_addr + PT_STAGES * PT_STAGE;            // epilogue scratch: 8 warps x 4 chunks x 2 doubles
+    const uint32_t bar_base = red_addr + 8 * 4 * 2 * 8;
+    const uint32_t bar_a_full = bar_base;                    // [STAGES] 8 producer warps arrive
+    const uint32_t bar_b_full = bar_a_full + 8 * PT_STAGES;  // [STAGES] TMA bytes
+    const uint32_t bar_empty = bar_b_full + 8 * PT_STAGES;   // [STAGES] MMA commit
+    const uint32_t bar_d_full = bar_empty + 8 * PT_STAGES;
+    const uint32_t tmem_slot = bar_d_full + 8;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw0));
+    double* red = reinterpret_cast<double*>(smem_raw + (red_addr - raw0));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * PT_M, co0 = blockIdx.y * PT_N, b = blockIdx.z;
+    const int nk = (p.Cin + PT_KC - 1) / PT_KC;
+    const int ncols = min(PT_N, (p.Cout - co0 + 15) & ~15);   // MMA N (multiple of 16)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PT_STAGES; ++s) {
+            mbar_init(bar_a_full + 8 * s, 8);
+            mbar_init(bar_b_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_d_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ============================================================ TMA: weight tiles (hi, lo) of every K chunk
+        if (lane == 0) {
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % PT_STAGES;
+                if (kc >= PT_STAGES) mbar_wait(bar_empty + 8 * s, ((kc / PT_STAGES) - 1) & 1);
+                const uint32_t dst = stage_addr + s * PT_STAGE + 2 * PT_A_PART, bar = bar_b_full + 8 * s;
+                mbar_expect_tx(bar, 2 * PT_B_PART);
+                tma_load_3d(dst, &map_wh, bar, kc * PT_KC, co0, 0);
+                tma_load_3d(dst + PT_B_PART, &map_wl, bar, kc * PT_KC, co0, 0);
+            }
+        }
+    } else if (warp == 1) {
+        // ============================================================ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = pt_idesc(ncols);
+            for (int kc = 0; kc < nk; ++kc) {
+                const int s = kc % PT_STAGES;
+                mbar_wait(bar_a_full + 8 * s, (kc / PT_STAGES) & 1);
+                mbar_wait(bar_b_full + 8 * s, (kc / PT_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t a_hi = stage_addr + s * PT_STAGE, a_lo = a_hi + PT_A_PART;
+                const uint32_t b_hi = a_hi + 2 * PT_A_PART, b_lo = b_hi + PT_B_PART;
+#pragma unroll
+                for (int term = 0; term < 3; ++term) {
+                    const uint32_t aa = (term == 2) ? a_lo : a_hi;      // Ah, Ah, Al
+                    const uint32_t bb = (term == 1) ? b_lo : b_hi;      // Bh, Bl, Bh
+#pragma unroll
+                    for (int ks = 0; ks < PT_KC / 16; ++ks)
+                        // A: MN-major, 16 channels = 16 rows of 128 B; halves of 64 points are PT_A_PART / 2 apart
+                        umma_ss(tmem, make_desc(aa + ks * 2048, PT_A_PART / 2), make_desc(bb + ks * 32, 16), idesc,
+                                (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                }
+                tc_commit(bar_empty + 8 * s);
+            }
+            tc_commit(bar_d_full);
+        }
+    } else {
+        // ============================================================ producers: activations -> FP16 hi/lo MN-major image
+        const int pw = warp - 2;                                 // 0..7: eight channels of every 64-channel chunk
+        const float* X = p.X + (long long)b * p.x_bstride;
+        const float* ia = p.in_a ? p.in_a + (long long)b * p.Cin : nullptr;
+        const float* is = p.in_s ? p.in_s + (long long)b * p.Cin : nullptr;
+        const int chunk = lane & 15;                             // 8 consecutive points
+        const int pt = n0 + chunk * 8;
+        const bool vec_ok = ((p.ldx & 3) == 0) && (pt + 7 < p.N) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+        for (int kc = 0; kc < nk; ++kc) {
+            const int s = kc % PT_STAGES;
+            if (kc >= PT_STAGES) mbar_wait(bar_empty + 8 * s, ((kc / PT_STAGES) - 1) & 1);
+            const uint32_t a_hi = stage_addr + s * PT_STAGE, a_lo = a_hi + PT_A_PART;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int cl = pw * 8 + t * 2 + (lane >> 4);     // channel within the chunk = row of the image
+                const int c = kc * PT_KC + cl;
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                if (c < p.Cin) {
+                    const float* src = X + (long long)c * p.ldx + pt;
+                    if (vec_ok) {
+                        const float4 u0 = __ldg(reinterpret_cast<const float4*>(src));
+                        const float4 u1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                        v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w; v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) if (pt + e < p.N) v[e] = __ldg(src + e);
+                    }
+                    if (ia) {
+                        const float av = __ldg(ia + c), sv = __ldg(is + c);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = (pt + e < p.N) ? pt_act(fmaf(av, v[e], sv), p.in_act) : 0.f;
+                    }
+                }
+                uint32_t hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                    const float2 hf = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                    hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+                    lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+                }
+                // image: [half = point / 64][row = channel][128 B = 64 points], 16-byte chunks XOR-swizzled by (row & 7)
+                const uint32_t off = (uint32_t)(chunk >> 3) * (PT_A_PART / 2) + (uint32_t)cl * 128u +
+                                     (uint32_t)(((chunk & 7) ^ (cl & 7)) << 4);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_a_full + 8 * s);
+        }
+
+        // ============================================================ epilogue: thread = point, 32 channels at a time
+        const int quarter = warp & 3, half = pw >> 2;            // TMEM lane quarter; columns [128 half, 128 half + 128)
+        const int row = quarter * 32 + lane;
+        const int n = n0 + row;
+        const bool nvalid = n < p.N;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const float* bias = p.bias ? p.bias + (long long)b * p.bias_bstride : nullptr;
+        mbar_wait(bar_d_full, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+            const int col = half * 128 + cc * 32;                // first column of the chunk (CTA-uniform per warp)
+            const int co_base = co0 + col;
+            double bs1 = 0.0, bs2 = 0.0;
+            if (col < ncols) {
+                uint32_t v[32];
+                tmem_ld32(tmem + lane_addr + (uint32_t)col, v);
+                tmem_ld_wait();
+                float y[32];
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int co = co_base + i;
+                    const bool cv = co < p.Cout;
+                    const float rs = cv ? __ldg(p.rscale + co) : 0.f;
+                    const float bv = (cv && bias) ? __ldg(bias + co) : 0.f;
+                    y[i] = __fadd_rn(__uint_as_float(v[i]) * rs, bv);
+                    if (cv && nvalid) { s1 += y[i]; s2 = fmaf(y[i], y[i], s2); }
+                }
+                if (p.Y) {
+                    float* Yb = p.Y + (long long)b * p.y_bstride;
+                    if (p.y_point_major) {
+                        if (nvalid) {
+                            float* o = Yb + (long long)n * p.ldy + co_base;
+                            if (co_base + 31 < p.Cout && ((p.ldy & 3) == 0)) {
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+                                    reinterpret_cast<float4*>(o)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) if (co_base + i < p.Cout) o[i] = y[i];
+                            }
+                        }
+                    } else if (nvalid) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (co_base + i < p.Cout) Yb[(long long)(co_base + i) * p.ldy + n] = y[i];   // lanes = consecutive points
+                    }
+                }
+                if (p.stats) { bs1 = warp_sum_d((double)s1); bs2 = warp_sum_d((double)s2); }
+                if (p.mm) {
+                    // max / min over the warp's 32 points of each of the 32 channels: recursive halving leaves channel
+                    // (lane-permuted) i in lane L with i = bit-reversed placement; 31 shuffles per quantity
+                    float mx[32], mn[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) { mx[i] = nvalid ? y[i] : -INFINITY; mn[i] = nvalid ? y[i] : INFINITY; }
+#pragma unroll
+                    for (int w = 16; w >= 1; w >>= 1) {
+                        const bool up = (lane & w) != 0;
+#pragma unroll
+                        for (int i = 0; i < w; ++i) {
+                            const float keep_mx = up ? mx[i + w] : mx[i], send_mx = up ? mx[i] : mx[i + w];
+                            const float keep_mn = up ? mn[i + w] : mn[i], send_mn = up ? mn[i] : mn[i + w];
+                            mx[i] = fmaxf(keep_mx, __shfl_xor_sync(0xffffffffu, send_mx, w));
+                            mn[i] = fminf(keep_mn, __shfl_xor_sync(0xffffffffu, send_mn, w));
+                        }
+                    }
+                    // lane L now holds channel index = L (bit k of L selected the upper half at width 2^k)
+                    float* mq = reinterpret_cast<float*>(smem_raw + (stage_addr - raw0)) + ((half * 4 + cc) * 4 + quarter) * 64;
+                    mq[lane * 2] = mx[0];
+                    mq[lane * 2 + 1] = mn[0];
+                }
+            }
+            if (p.stats && lane == 0) { red[((half * 4 + cc) * 4 + quarter) * 2] = bs1; red[((half * 4 + cc) * 4 + quarter) * 2 + 1] = bs2; }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        // combine the four quarters (fixed order) and publish the tile's partials
+        const int et = threadIdx.x - 64;                          // 0..255
+        if (p.stats && et < 8) {                                  // et = half * 4 + cc -> one 32-channel block
+            const int col = (et >> 2) * 128 + (et & 3) * 32;
+            const int blk = (co0 + col) >> 5, nblk = (p.Cout + 31) / 32;
+            if (col < ncols && blk < nblk) {
+                double t1 = 0.0, t2 = 0.0;
+                for (int q = 0; q < 4; ++q) { t1 += red[(et * 4 + q) * 2]; t2 += red[(et * 4 + q) * 2 + 1]; }
+                double* o = p.stats + (((long long)b * gridDim.x + blockIdx.x) * nblk + blk) * 2;
+                o[0] = t1; o[1] = t2;
+            }
+        }
+        if (p.mm) {
+            const int col = et;                                   // one channel of the tile per thread
+            const int co = co0 + col;
+            if (col < ncols && co < p.Cout) {
+                const float* mq = reinterpret_cast<const float*>(smem_raw + (stage_addr - raw0)) + ((col >> 5) * 4) * 64 + (col & 31) * 2;
+                float mxv = -INFINITY, mnv = INFINITY;
+                for (int q = 0; q < 4; ++q) { mxv = fmaxf(mxv, mq[q * 64]); mnv = fminf(mnv, mq[q * 64 + 1]); }
+                float* o = p.mm + (((long long)b * gridDim.x + blockIdx.x) * p.Cout + co) * 2;
+                o[0] = mxv; o[1] = mnv;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+    }
+}
+
+// One warp per weight row: k = exponent putting max|w| in [1024, 2048); hi/lo FP16 split of w * 2^k into rows of
+// cin_pad (zero padded) halves; rscale[row] = 2^-k.
+__global__ void pw_prep_weights_kernel(const float* __restrict__ W, int ldw, int Cout, int Cin, int cin_pad,
+                                       __half* __restrict__ Wh, __half* __restrict__ Wl, float* __restrict__ rscale) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= Cout) return;
+    const float* w = W + (long long)row * ldw;
+    float m = 0.f;
+    for (int c = lane; c < Cin; c += 32) m = fmaxf(m, fabsf(__ldg(w + c)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sc = 1.0f;
+    if (m > 0.f && m < 3.0e38f) {
+        int e;
+        frexpf(m, &e);
+        e = 11 - e;
+        e = e < -60 ? -60 : (e > 60 ? 60 : e);
+        sc = ldexpf(1.0f, e);
+    }
+    for (int c = lane; c < cin_pad; c += 32) {
+        const float v = c < Cin ? __ldg(w + c) * sc : 0.f;
+        const __half h = __float2half_rn(v);
+        Wh[(long long)row * cin_pad + c] = h;
+        Wl[(long long)row * cin_pad + c] = __float2half_rn(v - __half2float(h));
+    }
+    if (lane == 0) rscale[row] = 1.0f / sc;
+}
+
+// (rows, width) fp16 row-major weight matrix: box 64 channels x 256 rows, 128B swizzle, rows past the end read as zero
+static int make_map_w(CUtensorMap* m, const __half* base, int rows, int width) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return SED_ERR_UNSUPPORTED;
+    const cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)rows, 1};
+    const cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)rows * width * 2};
+    const cuuint32_t box[3] = {64, 256, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)base, dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? SED_OK : SED_ERR_CUDA_BASE - 1;
+}
+
+// Tensor-core implementation of pw_gemm (same arguments).  SED_ERR_UNSUPPORTED for shapes it does not cover.
+int pw_gemm_tc(const float* X, long long x_bstride, int ldx, const float* Wt, int ldw, const float* bias,
+               long long bias_bstride, const float* in_a, const float* in_s, int in_act, float* Y, long long y_bstride,
+               int ldy, int y_point_major, double* stats, float* mm, int B, int Cin, int Cout, int N, cudaStream_t st) {
+    if (Cin < 32 || Cin > 4096 || Cout <= 0) return SED_ERR_UNSUPPORTED;
+    const int cin_pad = (Cin + PT_KC - 1) / PT_KC * PT_KC;
+    const size_t wbytes = (size_t)Cout * cin_pad * sizeof(__half);
+    ensure_pool_config();
+    char* buf = nullptr;
+    SED_CUDA(cudaMallocAsync((void**)&buf, 2 * align_up(wbytes) + (size_t)Cout * sizeof(float), st));
+    __half* Wh = (__half*)buf;
+    __half* Wl = (__half*)(buf + align_up(wbytes));
+    float* rscale = (float*)(buf + 2 * align_up(wbytes));
+    pw_prep_weights_kernel<<<(Cout + 7) / 8, 256, 0, st>>>(Wt, ldw, Cout, Cin, cin_pad, Wh, Wl, rscale);
+    ++g_sed_launches;
+    CUtensorMap mh, ml;
+    int rc = make_map_w(&mh, Wh, Cout, cin_pad);
+    if (rc == SED_OK) rc = make_map_w(&ml, Wl, Cout, cin_pad);
+    if (rc == SED_OK) {
+        PtParams p{X, x_bstride, ldx, rscale, bias, bias_bstride, in_a, in_s, in_act, Y, y_bstride, ldy, y_point_major,
+                   stats, mm, Cin, Cout, N};
+        constexpr size_t smem = (size_t)PT_STAGES * PT_STAGE + 8 * 4 * 2 * 8 + 1024 + 256;
+        static_assert(smem <= 227 * 1024, "shared memory budget");
+        cudaError_t e = cudaFuncSetAttribute(pw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) rc = SED_ERR_CUDA_BASE - (int)e;
+        if (rc == SED_OK) {
+            dim3 grid((N + PT_M - 1) / PT_M, (Cout + PT_N - 1) / PT_N, B);
+            pw_tc_kernel<<<grid, PT_THREADS, smem, st>>>(mh, ml, p);
+            ++g_sed_launches;
+            e = cudaGetLastError();
+            if (e != cudaSuccess) rc = SED_ERR_CUDA_BASE - (int)e;
+        }
+    }
+    cudaFreeAsync(buf, st);
+    return rc;
+}
+
+}  // namespace sed
