@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the SED-Net inference hot path on B200 (contract: see the task statement / DESIGN.md section 6).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--prec 0|1|2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--prec 0|1|2|3]
 
 One "step" = one pass of the hot path over one batch of 8 synthetic 10 000-point clouds per GPU (BASELINE.json
 configs[1]): two SEDNet forwards (type net, instance net), type argmax, normalise, guarded mean-shift (50
@@ -235,16 +235,42 @@ def run_ours(args, rank, world, local_rank):
     flop_per_launch = BATCH * 2 * 2.0 * NPTS * NPTS * DIM
     t_launch = stage["shift"] / 1e3 / ITERS
     achieved = flop_per_launch / t_launch / 1e12
-    roof = {"kernel": {0: "ms_shift_ffma_kernel", 1: "ms_shift_tc_kernel(3xTF32)", 2: "ms_shift_tc_kernel(TF32)"}[args.prec],
-            "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-            "traffic": None, "peak_source": how + " dense bf16 sustained; the kernel computes in "
-            + ("FP32 FFMA (CUDA cores)" if args.prec == 0 else "TF32 on tcgen05 (half the bf16 rate)"),
+    # MMAs the kernel executes per algorithmic GEMM pair: FFMA none; split modes 3 (S) + 2 or 1 (PV); plain FP16 1 + 1
+    mma_per_pair = {0: 0, 1: 5, 2: 2, 3: 4}[args.prec]
+    kname = {0: "ms_shift_ffma_kernel", 1: "ms_shift_tc_kernel<3,2> (FP16 hi/lo split: S 3 MMAs, PV 2)",
+             2: "ms_shift_tc_kernel<1,1> (plain FP16)", 3: "ms_shift_tc_kernel<3,1> (FP16 hi/lo split: S 3 MMAs, PV 1)"}[args.prec]
+    roof = {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
+            "frac": achieved / tf_peak, "traffic": None,
+            "peak_source": how + " dense bf16 sustained (fp16 and bf16 share the tcgen05 rate)"
+            + ("; this mode runs on the CUDA cores" if args.prec == 0 else ""),
+            "executed_tflops": achieved * mma_per_pair / 2.0, "executed_frac": achieved * mma_per_pair / 2.0 / tf_peak,
+            "note": "achieved = algorithmic FLOP (2 GEMMs of 2*N*N*d per cloud and iteration) / measured launch time; the "
+                    "FP32-faithful split executes mma_per_pair/2 times that on the tensor pipe (executed_*)",
             "share_of_step": stage["shift"] / (ms_dev / args.steps)}
+    # BASELINE.json's second figure: kNN as distance-matrix-equivalent bandwidth (N*N*4 bytes per cloud and call, the
+    # matrix the reference materialises at src/PointNet.py:78-81 and this kernel never writes), timed alone
+    knn = None
+    if rank == 0:
+        xk = torch.randn((BATCH, 64, NPTS), device=dev)
+        idx = torch.empty((BATCH, NPTS, KNN), dtype=torch.int32, device=dev)
+        call = lambda: _lib.call("sed_knn_l2", _lib.ptr(xk), BATCH, 64, NPTS, KNN, _lib.ptr(idx), 0, _lib.stream())
+        for _ in range(3):
+            call()
+        ek0, ek1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ek0.record()
+        for _ in range(10):
+            call()
+        ek1.record()
+        torch.cuda.synchronize()
+        kms = ek0.elapsed_time(ek1) / 10
+        knn = {"kernel": "select_stream_kernel<L2> (C=64, k=64, batch of 8 clouds)", "ms_per_call": kms,
+               "dist_matrix_equiv_gbs": BATCH * NPTS * NPTS * 4.0 / (kms / 1e3) / 1e9, "hbm_peak_gbs": hbm_peak,
+               "note": "effective figure: the N x N matrix never exists; the kernel is bound by the selection ALU work"}
     if rank == 0:
         cpu = cpu_baseline_leg() if world == 1 and not args.no_cpu else None
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.prec == 0 else "tf32x3" if args.prec == 1 else "tf32",
+                "scaling": "weak", "vs_baseline": None, "dtype": {0: "f32", 1: "f16-split(3+2),f32-acc", 2: "f16,f32-acc", 3: "f16-split(3+1),f32-acc"}[args.prec],
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "clouds_per_gpu": BATCH, "points": NPTS, "k": KNN,
                            "ms_iterations": ITERS, "ms_prec_mode": args.prec, "parallelism": f"dp{world}",
@@ -252,7 +278,7 @@ def run_ours(args, rank, world, local_rank):
                            "guard_retries": retries},
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_host / args.steps},
-                "gpu_launches": n_launch, "clocks": clocks, "roofline": roof,
+                "gpu_launches": n_launch, "clocks": clocks, "roofline": roof, "knn": knn,
                 "stage_ms": stage}
         if cpu is not None:
             line["cpu_baseline"] = cpu
@@ -265,7 +291,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--prec", type=int, default=int(os.environ.get("SEDNET_B200_MS_PREC", "1")))
+    ap.add_argument("--prec", type=int, default=int(os.environ.get("SEDNET_B200_MS_PREC", "3")))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

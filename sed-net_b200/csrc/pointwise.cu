@@ -201,19 +201,23 @@ __global__ void gn_finalize_kernel(const double* __restrict__ part, int P, int N
                                    const float* __restrict__ gamma, const float* __restrict__ beta, int C, int G,
                                    float eps, float* __restrict__ a_out, float* __restrict__ s_out) {
     extern __shared__ double sh[];  // [G][2] mean, rstd
-    const int b = blockIdx.x;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // one warp per group: lanes stride over the (tile, block) partials, fixed-shape shuffle tree (deterministic)
+    for (int g = warp; g < G; g += nw) {
         double t1 = 0.0, t2 = 0.0;
-        for (int q = 0; q < P; ++q)
-            for (int k = 0; k < bpg; ++k) {
-                const double* o = part + (((long long)b * P + q) * NBLK + g * bpg + k) * 2;
-                t1 += o[0]; t2 += o[1];
-            }
-        const double mean = t1 / count;
-        double var = t2 / count - mean * mean;
-        var = var > 0.0 ? var : 0.0;
-        sh[2 * g] = mean;
-        sh[2 * g + 1] = 1.0 / sqrt(var + (double)eps);
+        for (int e = lane; e < P * bpg; e += 32) {
+            const int q = e / bpg, k = e - q * bpg;
+            const double* o = part + (((long long)b * P + q) * NBLK + g * bpg + k) * 2;
+            t1 += o[0]; t2 += o[1];
+        }
+        t1 = warp_sum_d(t1); t2 = warp_sum_d(t2);
+        if (lane == 0) {
+            const double mean = t1 / count;
+            double var = t2 / count - mean * mean;
+            var = var > 0.0 ? var : 0.0;
+            sh[2 * g] = mean;
+            sh[2 * g + 1] = 1.0 / sqrt(var + (double)eps);
+        }
     }
     __syncthreads();
     const int gs = C / G;

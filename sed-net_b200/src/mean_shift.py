@@ -11,7 +11,8 @@ MAX_CENTERS = 512
 
 class MeanShift:
     def __init__(self, prec_mode=None):
-        """prec_mode: 0 FP32 FFMA, 1 tcgen05 3xTF32, 2 tcgen05 TF32; None = $SEDNET_B200_MS_PREC or 0."""
+        """prec_mode of sed_ms_shift (include/sednet_b200.h): 0 FP32 FFMA, 1 / 3 tcgen05 FP16 hi/lo split (3+2 / 3+1 MMAs),
+        2 plain FP16; None = $SEDNET_B200_MS_PREC or 0."""
         import os
         self.prec_mode = int(os.environ.get("SEDNET_B200_MS_PREC", "0")) if prec_mode is None else prec_mode
 
