@@ -422,6 +422,8 @@ constexpr int SS_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 select (t
 constexpr int SS_NC = 64;         // candidates per tile
 constexpr int SS_CAP = 188;       // entries per row buffer (row-major; 752-B / 376-B row strides keep LDS.128 / LDS.64 conflict-free)
 constexpr int SS_WIN = 24;        // a prune leaves between k and k + SS_WIN entries
+constexpr int SS_SOFT = 124;      // soft mark: book a CTA-wide prune
+constexpr int SS_LAG = 3;         // ... this many tiles ahead
 constexpr int SS_STAGES = 3;
 constexpr int SS_NBUF = 4;        // TMEM buffers of 128 columns (two 64-column accumulators)
 constexpr int SS_XCRING = 8;      // candidate-norm slices in flight: >= SS_STAGES + SS_NBUF (producer's maximum lead)
@@ -589,12 +591,14 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
     const uint32_t bar_s_full = bar_x_empty + 8 * SS_STAGES;   // [SS_NBUF]
     const uint32_t bar_s_empty = bar_s_full + 8 * SS_NBUF;     // [SS_NBUF]
     const uint32_t tmem_slot = bar_s_empty + 8 * SS_NBUF;
+    const uint32_t sched_addr = tmem_slot + 8;                 // [16] tile index of a scheduled CTA-wide prune
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, q0 = blockIdx.x * ST_M;
     const int Nc = p.Nc;
     const int T = (Nc + SS_NC - 1) / SS_NC;
+    if (threadIdx.x < 16) sts_u32(sched_addr + threadIdx.x * 4, 0xffffffffu);
 
     if (threadIdx.x == 0) {
         mbar_init(bar_q_full, 1);
@@ -737,6 +741,18 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
             tmem_ld32(sb + 32, b0);                 // chunk 1 loads while chunk 0 is processed
             tmem_ld32(sb + 64 + 32, b1);
             const uint32_t xcs = xc_addr + (uint32_t)(j % SS_XCRING) * (SS_NC * 4);
+            // CTA-wide prunes: the four warps share the TMEM ring, so a warp that prunes alone stalls the others after
+            // ~2 tiles.  A warp whose buffers pass the soft mark books a prune SS_LAG tiles ahead (further than the
+            // warps can drift apart); every warp prunes when it reaches the booked tile.  The private prune of
+            // maybe_prune() stays as the overflow guard.
+            if (lds_u32(sched_addr + (uint32_t)(j & 15) * 4u) == (uint32_t)j) {
+                ss_prune<true>(key_addr, idx_addr, SS_CAP, k, SS_WIN, cnt, thr);
+            } else if (__any_sync(0xffffffffu, cnt > SS_SOFT)) {
+                bool booked = false;
+#pragma unroll
+                for (int d = 1; d <= SS_LAG; ++d) booked |= lds_u32(sched_addr + (uint32_t)((j + d) & 15) * 4u) == (uint32_t)(j + d);
+                if (!booked && lane == 0) sts_u32(sched_addr + (uint32_t)((j + SS_LAG) & 15) * 4u, (uint32_t)(j + SS_LAG));
+            }
             maybe_prune();
             process(a0, a1, j * SS_NC, xcs);
             tmem_ld_wait();
@@ -754,14 +770,20 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
             mbar_arrive(bar_s_empty + 8 * buf);    // every tcgen05.ld of tile j has completed (both waits above)
         }
 
-        // ---- exact top-k of the survivors, then one warp sorts each of its 32 rows
+        // ---- exact top-k of the survivors; the per-row counts go to shared memory (the Q tile is dead: every MMA
+        // completed before the last s_full) for the sort below
         ss_prune<true>(key_addr, idx_addr, SS_CAP, k, 0, cnt, thr);
-        __syncwarp();
-        for (int r = 0; r < 32; ++r) {
-            const int rr = quarter * 32 + r;
+        sts_u32(q_addr + (uint32_t)row * 4u, (uint32_t)cnt);
+    }
+    // ================================================================ sort: one warp per row, all six warps
+    __syncwarp();
+    asm volatile("bar.sync 2, 192;" ::: "memory");
+    {
+        const int k = p.k;
+        for (int rr = warp; rr < ST_M; rr += SS_THREADS / 32) {
             const int qq = q0 + rr;
-            const int rcnt = __shfl_sync(0xffffffffu, cnt, r);
             if (qq >= p.Nq) break;
+            const int rcnt = (int)lds_u32(q_addr + (uint32_t)rr * 4u);
             const uint32_t rk = list_addr + (uint32_t)rr * SS_KEY_ROW, ri = list_addr + SS_KEY_BYTES + (uint32_t)rr * SS_IDX_ROW;
             unsigned long long e[2];
 #pragma unroll
