@@ -106,7 +106,7 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
 
     if (warp == 0) {
         // ============================================================ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             for (int j = 0; j < T; ++j) {
                 const int s = j % STAGES;
                 if (j >= STAGES) mbar_wait(bar_x_empty + 8 * s, ((j / STAGES) - 1) & 1);
@@ -121,8 +121,8 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ============================================================ MMA issuer (one thread)
-        if (lane == 0) {
+        // ============================================================ MMA issuer (one elected thread)
+        if (elect_one()) {
             constexpr uint32_t IDESC_S = make_idesc(0), IDESC_PV = make_idesc(1);
             const uint32_t tmem_o = tmem + 256;
             // S(j) = sum over terms (a_part, b_part) of Q[a_part] X[b_part]^T, K = 128 channels = 8 steps of 16.

@@ -88,7 +88,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__
 
     if (warp == 0) {
         // ============================================================ TMA: weight tiles (hi, lo) of every K chunk
-        if (lane == 0) {
+        if (elect_one()) {
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % PT_STAGES;
                 if (kc >= PT_STAGES) mbar_wait(bar_empty + 8 * s, ((kc / PT_STAGES) - 1) & 1);
@@ -100,7 +100,7 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__
         }
     } else if (warp == 1) {
         // ============================================================ MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = pt_idesc(ncols);
             for (int kc = 0; kc < nk; ++kc) {
                 const int s = kc % PT_STAGES;

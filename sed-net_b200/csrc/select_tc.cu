@@ -126,7 +126,7 @@ select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_consta
 
     if (warp == 0) {
         // ============================================================ TMA producer
-        if (lane == 0 && J > 0) {
+        if (J > 0 && elect_one()) {
             mbar_expect_tx(bar_q_full, TILE2);
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) {
@@ -147,7 +147,7 @@ select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_consta
         }
     } else if (warp == 1) {
         // ============================================================ MMA issuer
-        if (lane == 0 && J > 0) {
+        if (J > 0 && elect_one()) {
             constexpr uint32_t IDESC = make_idesc(0);
             mbar_wait(bar_q_full, 0);
             for (int j = 0; j < J; ++j) {
@@ -617,7 +617,7 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
 
     if (warp == 0) {
         // ============================================================ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(bar_q_full, 2 * QPART);
             tma_load_3d(q_addr, &map_qh, bar_q_full, 0, q0, b);
             tma_load_3d(q_addr + QPART, &map_ql, bar_q_full, 0, q0, b);
@@ -636,7 +636,7 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
         }
     } else if (warp == 1) {
         // ============================================================ MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t IDESC = make_idesc_n(0, SS_NC);
             mbar_wait_relaxed<32>(bar_q_full, 0);
             for (int j = 0; j < T; ++j) {
@@ -902,7 +902,7 @@ kth_stream_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
 
     if (warp == 0) {
         // ============================================================ TMA producer
-        if (lane == 0) {
+        if (elect_one()) {
             for (int j = 0; j < T; ++j) {
                 const int s = j % KS_STAGES;
                 if (j >= KS_STAGES) mbar_wait_relaxed<256>(bar_x_empty + 8 * s, ((j / KS_STAGES) - 1) & 1);
@@ -916,7 +916,7 @@ kth_stream_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
         }
     } else if (warp == 1) {
         // ============================================================ MMA issuer
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t IDESC = make_idesc_n(0, SS_NC);
             mbar_wait_relaxed<32>(bar_q_full, 0);
             for (int j = 0; j < T; ++j) {

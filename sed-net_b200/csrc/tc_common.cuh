@@ -46,6 +46,13 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// true in exactly one lane of a converged warp (the compiler then issues tcgen05 / TMA instructions without a
+// per-instruction election loop)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
