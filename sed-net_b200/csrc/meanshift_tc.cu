@@ -52,7 +52,8 @@ struct TcParams {
 };
 
 // NS: MMAs per S tile (1 or 3); NV: MMAs per PV tile (1 or 2)
-template <int NS, int NV>
+// KT: kernel type (0 gaussian, 1 epanechnikov)
+template <int NS, int NV, int KT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, TcParams p) {
     constexpr bool HAS_LO = (NS > 1) || (NV > 1);
@@ -226,7 +227,7 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float p0, p1;
-                    if (p.kernel_type == 0) {
+                    if (KT == 0) {
                         p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), c1, c0));
                         p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), c1, c0));
                     } else {
@@ -372,17 +373,22 @@ __global__ void split_f16_kernel(const float* __restrict__ x, long long n, __hal
     if (lo) *reinterpret_cast<uint2*>(lo + i) = *reinterpret_cast<const uint2*>(l);
 }
 
-template <int NS, int NV>
-static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const TcParams& p, int B, cudaStream_t st) {
+template <int NS, int NV, int KT>
+static int launch_tc_k(const CUtensorMap& xh, const CUtensorMap& xl, const TcParams& p, int B, cudaStream_t st) {
     constexpr bool HAS_LO = (NS > 1) || (NV > 1);
     constexpr int STAGES = HAS_LO ? 3 : 6;
     constexpr size_t smem = (size_t)STAGES * (HAS_LO ? 2 : 1) * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-    auto kern = ms_shift_tc_kernel<NS, NV>;
+    auto kern = ms_shift_tc_kernel<NS, NV, KT>;
     SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     (void)B;
     kern<<<p.grid_ctas, TC_THREADS, smem, st>>>(xh, xl, p);
     SED_CHECK_LAUNCH();
     return SED_OK;
+}
+
+template <int NS, int NV>
+static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const TcParams& p, int B, cudaStream_t st) {
+    return p.kernel_type == 0 ? launch_tc_k<NS, NV, 0>(xh, xl, p, B, st) : launch_tc_k<NS, NV, 1>(xh, xl, p, B, st);
 }
 
 int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type, int prec_mode,
