@@ -361,3 +361,98 @@ def test_pipeline_vs_oracle(dev):
     stage, retries = pipe.stage_ms()
     assert all(v >= 0 for v in stage.values())
     pipe.close()
+
+
+# ------------------------------------------------------------------------------------------------ round-1 kernels
+@pytest.mark.parametrize("prec", [1, 3])
+@pytest.mark.parametrize("n,npatch,sigma,kernel", [(777, 3, 0.02, "gaussian"), (2048, 9, 0.02, "gaussian"),
+                                                   (1500, 5, 0.01, "epa"), (4100, 8, 0.01, "gaussian")])
+def test_meanshift_tensor_core_modes_vs_oracle(dev, prec, n, npatch, sigma, kernel):
+    """tcgen05 mean-shift (FP16 hi/lo split operands, FP32 accumulation) against the oracle: identical partition,
+    shifted points within 1e-4 (measured: <= 1e-5); covers the key-split of the partial last wave (small N) and N
+    that is no multiple of the 128-row / 128-key tiles."""
+    from sednet_b200.src.mean_shift import MeanShift
+    _, _, lab, _, _ = synth.make_cloud(900 + n, n, n_patches=npatch, min_pts=170)
+    X = t(synth.make_embedding(lab, 128, sigma, n))
+    with torch.no_grad():
+        onew, ocen, obw, olab = O.mean_shift(X, 10000, 0.015, 20, kernel)
+    newX, center, bw, labels = MeanShift(prec_mode=prec).mean_shift(X.to(dev), 10000, 0.015, 20, kernel_type=kernel)
+    assert float((newX.cpu() - onew).abs().max()) < 1e-4
+    assert (canon(labels.cpu().numpy()) == canon(olab.numpy())).all()
+    assert float((torch.linalg.norm(newX, dim=1) - 1).abs().max()) < 1e-5
+
+
+def test_meanshift_tensor_core_batched_matches_single(dev):
+    """sed_ms_shift over a batch gives, cloud by cloud, what single-cloud calls give.  The decomposition into CTAs
+    (whole query tiles + key-split remainder, meanshift_tc.cu) depends on the batch, and a key-split sums its partial
+    accumulators in a fixed but different order: agreement to FP32 rounding, not bit-for-bit."""
+    import ctypes as C
+    from sednet_b200.src import _lib
+    B, N, d = 3, 3000, 128
+    Xs = []
+    for b in range(B):
+        _, _, lab, _, _ = synth.make_cloud(50 + b, N, n_patches=6, min_pts=170)
+        Xs.append(t(synth.make_embedding(lab, d, 0.02, b)))
+    X = torch.stack(Xs).to(dev).contiguous()
+    bw = torch.tensor([0.25, 0.3, 0.35], device=dev)
+    out, tmp = torch.empty_like(X), torch.empty_like(X)
+    _lib.call("sed_ms_shift", _lib.ptr(X), _lib.ptr(bw), B, N, d, 7, 0, 3, _lib.ptr(out), _lib.ptr(tmp), _lib.stream())
+    for b in range(B):
+        o1, t1 = torch.empty_like(X[b]), torch.empty_like(X[b])
+        _lib.call("sed_ms_shift", _lib.ptr(X[b]), _lib.ptr(bw[b:b + 1]), 1, N, d, 7, 0, 3, _lib.ptr(o1), _lib.ptr(t1),
+                  _lib.stream())
+        assert float((o1 - out[b]).abs().max()) < 2e-6
+
+
+def test_knn_heavy_ties(dev):
+    """Duplicated points: every row has far more than k candidates at the k-th distance.  Ties go to the lowest
+    candidate index (the rule of this implementation; torch.topk leaves the order of equal values unspecified), so the
+    result is fully determined and the selected distances must equal the oracle's."""
+    from sednet_b200.src import PointNet
+    rng = np.random.default_rng(3)
+    base = rng.normal(size=(16, 40)).astype(np.float32)               # 40 distinct points in 16-d
+    rep = np.repeat(np.arange(40), 60)                                 # each repeated 60 times -> N = 2400
+    rng.shuffle(rep)
+    x = base[:, rep][None].copy()
+    k = 64                                                              # > 60 copies: the 61st.. neighbours tie as well
+    idx = PointNet.knn(t(x).to(dev), k, k).cpu().numpy()[0]
+    ref = O.knn_l2(t(x), k).numpy()[0]
+    xd = x[0].astype(np.float64)
+    for r in range(0, 2400, 37):
+        d = ((xd - xd[:, r:r + 1]) ** 2).sum(0)
+        assert np.allclose(np.sort(d[idx[r]]), np.sort(d[ref[r]]), rtol=0, atol=1e-9)
+        same = np.flatnonzero(rep == rep[r])
+        assert set(same).issubset(set(idx[r]))                         # all 60 copies of the point itself
+        assert len(set(idx[r])) == k
+    # exact-duplicate rows (distance 0 to 59 others): the zero-distance block is the 60 copies in ascending index order
+    r = int(np.flatnonzero(rep == rep[0])[5])
+    zero = [i for i in idx[r] if rep[i] == rep[r]]
+    assert sorted(zero) == list(np.flatnonzero(rep == rep[r]))
+
+
+@pytest.mark.parametrize("quantile", [0.015, 0.0262])
+def test_bandwidth_streaming_and_fallback(dev, quantile):
+    """K = int(quantile * 10000) = 150 runs the streaming K-th-score kernel, 262 the multi-pass radix select."""
+    from sednet_b200.src.mean_shift import MeanShift
+    _, _, lab, _, _ = synth.make_cloud(31, 3000, n_patches=7, min_pts=300)
+    X = t(synth.make_embedding(lab, 128, 0.03, 9))
+    ref = float(O.ms_bandwidth(X, 10000, quantile))
+    got = float(MeanShift(0).compute_bandwidth(X.to(dev), 10000, quantile))
+    assert abs(got - ref) < 1e-4 * ref
+
+
+def test_pipeline_split_precision_mode(dev):
+    """The end-to-end step in the bench's default mean-shift mode (3) gives the oracle's segmentation."""
+    from sednet_b200.pipeline import Pipeline
+    B, N, k = 2, 1500, 32
+    pts, nrm, lab, typ = synth.make_batch(B, N, seed0=4321, n_patches=5)
+    sd_t, sd_i = synth.make_state_dict(0), synth.make_state_dict(1, randomize_gn=True)
+    pipe = Pipeline(B, N, k)
+    pipe.set_weights(sd_t, sd_i)
+    out = {kk: v.clone() for kk, v in pipe.run_host(t(pts).pin_memory(), t(nrm).pin_memory(), 0.015, 50, 3).items()}
+    ref0 = pipe.run_host(t(pts).pin_memory(), t(nrm).pin_memory(), 0.015, 50, 0)
+    for b in range(B):
+        assert (canon(out["labels"][b].numpy()) == canon(ref0["labels"][b].numpy())).all()
+        assert np.array_equal(out["pred_type"][b].numpy(), ref0["pred_type"][b].numpy())
+        assert abs(float(out["bw"][b]) - float(ref0["bw"][b])) == 0.0
+    pipe.close()
