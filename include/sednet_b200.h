@@ -122,6 +122,14 @@ int sed_sednet_forward(const float* const* params_host, const float* points, int
                        float* log_prob, float* edges, float* x4, float* x_features, void* workspace,
                        int64_t workspace_bytes, sed_stream_t stream);
 
+/* Same forward with the first EdgeConv layer's neighbour table given: idx1 (B,N,k) int32 = sed_knn_pn(points, ..., k,
+ * normal_metric_W, idx64 = 0).  That table depends on the input only, so a driver that runs several networks on the
+ * same clouds (type net and instance net, generate_predictions_aug.py:224-229) builds it once.  idx1 NULL = compute. */
+int sed_sednet_forward_g1(const float* const* params_host, const float* points, const int* idx1, int B, int N, int k,
+                          float normal_metric_W, float w_pos_enc, int emb_size, int num_primitives, float* embedding,
+                          float* log_prob, float* edges, float* x4, float* x_features, void* workspace,
+                          int64_t workspace_bytes, sed_stream_t stream);
+
 /* One EdgeConv block, src/SEDNet.py:37-45,81-92: Conv2d(2C->Cout,1x1,no bias) over cat([x_j-x_i, x_i]) ->
  * GroupNorm(G) -> LeakyReLU(slope) -> max over k.  x (B,Cin,N) with batch stride x_bstride elements,
  * idx (B,N,k) int32, W (Cout,2Cin), out (B,Cout,N) with batch stride out_bstride.  Cout in {64,128}.
@@ -237,9 +245,10 @@ int sed_pipeline_run_host(sed_pipeline_t* p, const float* points_host, const flo
 int sed_pipeline_run_device(sed_pipeline_t* p, const float* points_dev, const float* normals_dev, int B,
                             double quantile, int iterations, int prec_mode, sed_stream_t stream);
 void* sed_pipeline_device_ptr(sed_pipeline_t* p, const char* name);
-/* device time (ms, CUDA events on the run's stream) of the stages of the last run: forward(type net),
- * forward(instance net)+normalise, bandwidth, shift iterations, nms (+ guard retries), type vote + fits +
- * residuals; retries = number of guard re-runs. Waits for the run to finish. */
+/* device time (ms, CUDA events on the run's stream) of the stages of the last run: first-layer graph (shared by the
+ * two networks), both forwards (type net on an internal side stream, concurrently with the instance net) +
+ * normalise, bandwidth, shift iterations, nms (+ guard retries), type vote + fits + residuals; retries = number of
+ * guard re-runs. Waits for the run to finish. */
 int sed_pipeline_stage_ms(sed_pipeline_t* p, float* ms6_host, int* retries_host);
 /* number of kernels the library launched since the last call with reset != 0 (for bench accounting). */
 int64_t sed_launch_count(int reset);

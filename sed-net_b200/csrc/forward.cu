@@ -119,6 +119,14 @@ int64_t sed_sednet_workspace_bytes(int B, int N, int k) {
 int sed_sednet_forward(const float* const* P, const float* points, int B, int N, int k, float normal_metric_W,
                        float w_pos_enc, int E, int NP, float* embedding, float* log_prob, float* edges, float* x4_out,
                        float* feats_out, void* workspace, int64_t workspace_bytes, sed_stream_t stream) {
+    return sed_sednet_forward_g1(P, points, nullptr, B, N, k, normal_metric_W, w_pos_enc, E, NP, embedding, log_prob,
+                                 edges, x4_out, feats_out, workspace, workspace_bytes, stream);
+}
+
+int sed_sednet_forward_g1(const float* const* P, const float* points, const int* idx1, int B, int N, int k,
+                          float normal_metric_W, float w_pos_enc, int E, int NP, float* embedding, float* log_prob,
+                          float* edges, float* x4_out, float* feats_out, void* workspace, int64_t workspace_bytes,
+                          sed_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!P || !points || !embedding || !log_prob || !edges || !workspace) return SED_ERR_ARG;
     if (B <= 0 || N < k || k <= 0 || k > 256 || E <= 0 || E > 256 || NP <= 0 || NP > 8) return SED_ERR_ARG;
@@ -131,8 +139,10 @@ int sed_sednet_forward(const float* const* P, const float* points, int B, int N,
     const long long fb = 256LL * N;  // batch stride of feats
 
     // ---- encoder: three EdgeConv blocks (src/SEDNet.py:80-92)
-    SED_TRY(knn_pn(points, 6LL * N, B, N, k, normal_metric_W, w.idx, 0, st));
-    SED_TRY(edgeconv(points, 6LL * N, w.idx, P[SED_P_ENC_CONV1_W], P[SED_P_ENC_BN1_W], P[SED_P_ENC_BN1_B], B, 6, 64, N,
+    // (the first layer's graph depends on the input only: a caller running several networks on the same clouds
+    // computes it once with sed_knn_pn and passes it in)
+    if (!idx1) SED_TRY(knn_pn(points, 6LL * N, B, N, k, normal_metric_W, w.idx, 0, st));
+    SED_TRY(edgeconv(points, 6LL * N, idx1 ? idx1 : w.idx, P[SED_P_ENC_CONV1_W], P[SED_P_ENC_BN1_W], P[SED_P_ENC_BN1_B], B, 6, 64, N,
                      k, 2, kGnEps, 0.2f, w.feats, fb, w.e, st));
     SED_TRY(knn_l2(w.feats, fb, B, 64, N, k, w.idx, 0, st));
     SED_TRY(edgeconv(w.feats, fb, w.idx, P[SED_P_ENC_CONV2_W], P[SED_P_ENC_BN2_W], P[SED_P_ENC_BN2_B], B, 64, 64, N, k,

@@ -65,14 +65,19 @@ struct sed_pipeline {
     const float* wptr[2][SED_P_COUNT];
     bool have_weights;
     // device buffers
-    float *pts, *nrm, *inp, *emb, *logp, *edges, *X, *shifted, *tmp, *kth, *bw, *centers, *params, *residual;
+    float *pts, *nrm, *inp, *emb, *logp, *edges, *emb2, *logp2, *edges2, *X, *shifted, *tmp, *kth, *bw, *centers, *params,
+        *residual;
     long long* labels;
-    int *pred_type, *seg_type, *seg_count, *status, *center_ids, *n_centers, *n_labels;
-    void *fwd_ws, *nms_ws;
+    int *pred_type, *seg_type, *seg_count, *status, *center_ids, *n_centers, *n_labels, *idx1;
+    void *fwd_ws, *fwd_ws2, *nms_ws;
     int64_t fwd_ws_bytes;
+    // the type network runs on its own stream, concurrently with the instance network (both read the same input and the
+    // same first-layer graph; the tails of one network's kernels overlap the other's)
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_join;
     // pinned host scratch
     int* h_counts;  // [2*max_B]: n_labels, n_centers
-    // stage boundaries of the last run: start, fwd(type), fwd(inst)+normalise, bandwidth, shift, nms, fits
+    // stage boundaries of the last run: start, first-layer graph, both forwards + normalise, bandwidth, shift, nms, fits
     cudaEvent_t ev[7];
     int retries;
 };
@@ -102,14 +107,18 @@ int64_t sed_launch_count(int reset) {
 
 void sed_pipeline_destroy(sed_pipeline_t* p) {
     if (!p) return;
-    void* bufs[] = {p->wbuf[0], p->wbuf[1], p->pts, p->nrm, p->inp, p->emb, p->logp, p->edges, p->X, p->shifted, p->tmp,
-                    p->kth, p->bw, p->centers, p->params, p->residual, p->labels, p->pred_type, p->seg_type,
-                    p->seg_count, p->status, p->center_ids, p->n_centers, p->n_labels, p->fwd_ws, p->nms_ws};
+    void* bufs[] = {p->wbuf[0], p->wbuf[1], p->pts, p->nrm, p->inp, p->emb, p->logp, p->edges, p->emb2, p->logp2, p->edges2,
+                    p->X, p->shifted, p->tmp, p->kth, p->bw, p->centers, p->params, p->residual, p->labels, p->pred_type,
+                    p->seg_type, p->seg_count, p->status, p->center_ids, p->n_centers, p->n_labels, p->idx1, p->fwd_ws,
+                    p->fwd_ws2, p->nms_ws};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (p->h_counts) cudaFreeHost(p->h_counts);
     for (auto& e : p->ev)
         if (e) cudaEventDestroy(e);
+    if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    if (p->side) cudaStreamDestroy(p->side);
     delete p;
 }
 
@@ -128,6 +137,8 @@ int sed_pipeline_create(int max_B, int N, int k, int max_segments, sed_pipeline_
     PALLOC(wbuf[0], wtot); PALLOC(wbuf[1], wtot);
     PALLOC(pts, B * n * 3 * 4); PALLOC(nrm, B * n * 3 * 4); PALLOC(inp, B * 6 * n * 4);
     PALLOC(emb, B * p->E * n * 4); PALLOC(logp, B * p->NP * n * 4); PALLOC(edges, B * 2 * n * 4);
+    PALLOC(emb2, B * p->E * n * 4); PALLOC(logp2, B * p->NP * n * 4); PALLOC(edges2, B * 2 * n * 4);
+    PALLOC(idx1, B * n * (size_t)k * 4); PALLOC(fwd_ws2, p->fwd_ws_bytes);
     PALLOC(X, B * n * d * 4); PALLOC(shifted, B * n * d * 4); PALLOC(tmp, B * n * d * 4);
     PALLOC(kth, B * n * 4); PALLOC(bw, B * 4); PALLOC(centers, B * S * d * 4);
     PALLOC(params, B * S * SED_FIT_PARAMS * 4); PALLOC(residual, B * S * 4);
@@ -138,6 +149,9 @@ int sed_pipeline_create(int max_B, int N, int k, int max_segments, sed_pipeline_
     if (rc == SED_OK && cudaMallocHost((void**)&p->h_counts, 2 * B * sizeof(int)) != cudaSuccess) rc = SED_ERR_CUDA_BASE - 2;
     for (auto& e : p->ev)
         if (rc == SED_OK && cudaEventCreate(&e) != cudaSuccess) rc = SED_ERR_CUDA_BASE - 2;
+    if (rc == SED_OK && cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking) != cudaSuccess) rc = SED_ERR_CUDA_BASE - 2;
+    if (rc == SED_OK && cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = SED_ERR_CUDA_BASE - 2;
+    if (rc == SED_OK && cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) rc = SED_ERR_CUDA_BASE - 2;
     if (rc != SED_OK) { sed_pipeline_destroy(p); return rc; }
     *out = p;
     return SED_OK;
@@ -187,14 +201,22 @@ int sed_pipeline_run_device(sed_pipeline_t* p, const float* points_dev, const fl
     SED_CUDA(cudaEventRecord(p->ev[0], st));
     pack_input_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(points_dev, normals_dev, N, p->inp);
     SED_CHECK_LAUNCH();
-    // type network, then instance network (generate_predictions_aug.py:224-229); only the outputs the driver keeps
-    SED_TRY(sed_sednet_forward(p->wptr[0], p->inp, B, N, p->k, 1.0f, 0.2f, p->E, p->NP, p->emb, p->logp, p->edges, nullptr,
-                               nullptr, p->fwd_ws, p->fwd_ws_bytes, st));
-    SED_TRY(sed_segment_types(p->logp, nullptr, B, p->NP, N, S, p->pred_type, nullptr, nullptr, st));
+    // first EdgeConv layer's graph: a function of the input only (src/SEDNet.py:80, src/PointNet.py:90-137), shared by
+    // the two networks
+    SED_TRY(sed_knn_pn(p->inp, B, N, p->k, 1.0f, p->idx1, 0, st));
     SED_CUDA(cudaEventRecord(p->ev[1], st));
-    SED_TRY(sed_sednet_forward(p->wptr[1], p->inp, B, N, p->k, 1.0f, 0.2f, p->E, p->NP, p->emb, p->logp, p->edges, nullptr,
-                               nullptr, p->fwd_ws, p->fwd_ws_bytes, st));
+    // type network (side stream) and instance network (generate_predictions_aug.py:224-229); only the outputs the
+    // driver keeps
+    SED_CUDA(cudaEventRecord(p->ev_fork, st));
+    SED_CUDA(cudaStreamWaitEvent(p->side, p->ev_fork, 0));
+    SED_TRY(sed_sednet_forward_g1(p->wptr[0], p->inp, p->idx1, B, N, p->k, 1.0f, 0.2f, p->E, p->NP, p->emb2, p->logp2,
+                                  p->edges2, nullptr, nullptr, p->fwd_ws2, p->fwd_ws_bytes, p->side));
+    SED_TRY(sed_segment_types(p->logp2, nullptr, B, p->NP, N, S, p->pred_type, nullptr, nullptr, p->side));
+    SED_CUDA(cudaEventRecord(p->ev_join, p->side));
+    SED_TRY(sed_sednet_forward_g1(p->wptr[1], p->inp, p->idx1, B, N, p->k, 1.0f, 0.2f, p->E, p->NP, p->emb, p->logp,
+                                  p->edges, nullptr, nullptr, p->fwd_ws, p->fwd_ws_bytes, st));
     SED_TRY(sed_normalize_transpose(p->emb, B, p->E, N, p->X, st));
+    SED_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
     SED_CUDA(cudaEventRecord(p->ev[2], st));
     // guarded mean-shift: re-run a cloud with quantile * 1.2 while it has more than 49 labels
     SED_TRY(pipe_mean_shift(p, 0, B, (double)quantile, iterations, prec_mode, true, st));
@@ -260,6 +282,7 @@ void* sed_pipeline_device_ptr(sed_pipeline_t* p, const char* name) {
     if (!p || !name) return nullptr;
     struct { const char* n; void* v; } tab[] = {
         {"points", p->pts}, {"normals", p->nrm}, {"input", p->inp}, {"embedding", p->emb}, {"log_prob", p->logp},
+        {"type_log_prob", p->logp2}, {"graph1", p->idx1},
         {"edges", p->edges}, {"X", p->X}, {"shifted", p->shifted}, {"bw", p->bw}, {"centers", p->centers},
         {"params", p->params}, {"residual", p->residual}, {"labels", p->labels}, {"pred_type", p->pred_type},
         {"seg_type", p->seg_type}, {"seg_count", p->seg_count}, {"status", p->status}, {"center_ids", p->center_ids},

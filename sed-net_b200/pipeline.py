@@ -79,7 +79,7 @@ class Pipeline:
         _lib.call("sed_pipeline_run_device", self._h, _lib.ptr(points), _lib.ptr(normals), B, float(quantile),
                   int(iterations), int(prec_mode), _lib.stream())
 
-    STAGES = ("forward_type", "forward_inst", "bandwidth", "shift", "nms", "fit")
+    STAGES = ("graph1", "forwards", "bandwidth", "shift", "nms", "fit")
 
     def stage_ms(self):
         """Device time of each stage of the last run (CUDA events on the run's stream) and the guard retries."""
@@ -91,7 +91,7 @@ class Pipeline:
                    params=("BS8", torch.float32), status=("BS", torch.int32), residual=("BS", torch.float32),
                    bw=("B", torch.float32), n_labels=("B", torch.int32), n_centers=("B", torch.int32),
                    X=("BNd", torch.float32), shifted=("BNd", torch.float32), embedding=("BdN", torch.float32),
-                   log_prob=("B6N", torch.float32))
+                   log_prob=("B6N", torch.float32), type_log_prob=("B6N", torch.float32))
 
     def device_tensor_view(self, name):
         """Zero-copy torch view of a named device buffer of the handle (valid for the handle's lifetime)."""

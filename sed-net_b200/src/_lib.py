@@ -24,6 +24,8 @@ SIGNATURES = {
     "sed_sednet_workspace_bytes": (L, [I, I, I]),
     "sed_sednet_forward": (I, [C.POINTER(C.c_void_p), c_f32p, I, I, I, F, F, I, I, c_f32p, c_f32p, c_f32p, c_f32p,
                                c_f32p, c_vp, L, c_vp]),
+    "sed_sednet_forward_g1": (I, [C.POINTER(C.c_void_p), c_f32p, c_i32p, I, I, I, F, F, I, I, c_f32p, c_f32p, c_f32p,
+                                  c_f32p, c_f32p, c_vp, L, c_vp]),
     "sed_edgeconv_workspace_bytes": (L, [I, I, I]),
     "sed_edgeconv_forward": (I, [c_f32p, L, c_i32p, c_f32p, c_f32p, c_f32p, I, I, I, I, I, I, F, F, c_f32p, L, c_vp,
                                  c_vp]),
