@@ -239,8 +239,12 @@ def run_ours(args, rank, world, local_rank):
     mma_per_pair = {0: 0, 1: 5, 2: 2, 3: 4}[args.prec]
     kname = {0: "ms_shift_ffma_kernel", 1: "ms_shift_tc_kernel<3,2> (FP16 hi/lo split: S 3 MMAs, PV 2)",
              2: "ms_shift_tc_kernel<1,1> (plain FP16)", 3: "ms_shift_tc_kernel<3,1> (FP16 hi/lo split: S 3 MMAs, PV 1)"}[args.prec]
+    # DRAM bytes of one launch (dram__bytes_read.sum + dram__bytes_write.sum of the `ncu --set full` capture of this
+    # kernel at this shape, B = 8: profiles/ms_shift_tc_r1c.md); other modes were not captured
+    traffic = {3: 82.010368e6 + 16.861440e6}.get(args.prec)
     roof = {"kernel": kname, "bound": "tensor", "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s",
-            "frac": achieved / tf_peak, "traffic": None,
+            "frac": achieved / tf_peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu, profiles/ms_shift_tc_r1c.md)",
+            "algorithmic_bytes_per_launch": BATCH * 3.0 * NPTS * DIM * 4,
             "peak_source": how + " dense bf16 sustained (fp16 and bf16 share the tcgen05 rate)"
             + ("; this mode runs on the CUDA cores" if args.prec == 0 else ""),
             "executed_tflops": achieved * mma_per_pair / 2.0, "executed_frac": achieved * mma_per_pair / 2.0 / tf_peak,

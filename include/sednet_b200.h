@@ -130,6 +130,12 @@ int sed_sednet_forward_g1(const float* const* params_host, const float* points, 
                           float* log_prob, float* edges, float* x4, float* x_features, void* workspace,
                           int64_t workspace_bytes, sed_stream_t stream);
 
+/* src/SEDNet.py:78-98  DGCNNEncoderGn.forward (mode 5) alone: points (B,6,N) -> x4 (B,1024), x_features (B,256,N).
+ * Only the encoder entries of the parameter table (SED_P_ENC_*) are read.  Workspace as for sed_sednet_forward. */
+int sed_encoder_forward(const float* const* params_host, const float* points, int B, int N, int k,
+                        float normal_metric_W, float* x4, float* x_features, void* workspace, int64_t workspace_bytes,
+                        sed_stream_t stream);
+
 /* One EdgeConv block, src/SEDNet.py:37-45,81-92: Conv2d(2C->Cout,1x1,no bias) over cat([x_j-x_i, x_i]) ->
  * GroupNorm(G) -> LeakyReLU(slope) -> max over k.  x (B,Cin,N) with batch stride x_bstride elements,
  * idx (B,N,k) int32, W (Cout,2Cin), out (B,Cout,N) with batch stride out_bstride.  Cout in {64,128}.

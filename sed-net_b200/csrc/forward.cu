@@ -84,6 +84,31 @@ static int conv_gn(const float* X, long long x_bstride, const float* W, int ldw,
     return SED_OK;
 }
 
+// DGCNNEncoderGn.forward, mode 5 (src/SEDNet.py:78-98): leaves x_features in w.feats and x4 in w.x4.
+static int encoder(const float* const* P, const float* points, const int* idx1, int B, int N, int k,
+                   float normal_metric_W, FwdWs& w, cudaStream_t st) {
+    const long long fb = 256LL * N;  // batch stride of feats
+    // ---- encoder: three EdgeConv blocks (src/SEDNet.py:80-92)
+    // (the first layer's graph depends on the input only: a caller running several networks on the same clouds
+    // computes it once with sed_knn_pn and passes it in)
+    if (!idx1) SED_TRY(knn_pn(points, 6LL * N, B, N, k, normal_metric_W, w.idx, 0, st));
+    SED_TRY(edgeconv(points, 6LL * N, idx1 ? idx1 : w.idx, P[SED_P_ENC_CONV1_W], P[SED_P_ENC_BN1_W], P[SED_P_ENC_BN1_B], B, 6, 64, N,
+                     k, 2, kGnEps, 0.2f, w.feats, fb, w.e, st));
+    SED_TRY(knn_l2(w.feats, fb, B, 64, N, k, w.idx, 0, st));
+    SED_TRY(edgeconv(w.feats, fb, w.idx, P[SED_P_ENC_CONV2_W], P[SED_P_ENC_BN2_W], P[SED_P_ENC_BN2_B], B, 64, 64, N, k,
+                     2, kGnEps, 0.2f, w.feats + 64LL * N, fb, w.e, st));
+    SED_TRY(knn_l2(w.feats + 64LL * N, fb, B, 64, N, k, w.idx, 0, st));
+    SED_TRY(edgeconv(w.feats + 64LL * N, fb, w.idx, P[SED_P_ENC_CONV3_W], P[SED_P_ENC_BN3_W], P[SED_P_ENC_BN3_B], B, 64,
+                     128, N, k, 2, kGnEps, 0.2f, w.feats + 128LL * N, fb, w.e, st));
+
+    // ---- mlp1 + GroupNorm(8) + ReLU + max over N (src/SEDNet.py:95-96); the (B,1024,N) tensor is never written
+    SED_TRY(conv_gn(w.feats, fb, P[SED_P_ENC_MLP1_W], 256, P[SED_P_ENC_MLP1_B], 0, nullptr, nullptr, 0, nullptr, B, 256,
+                    1024, N, 8, P[SED_P_ENC_BNMLP1_W], P[SED_P_ENC_BNMLP1_B], w.a[0], w.s[0], w, w.mm, st));
+    SED_TRY(pool_finalize(w.mm, (N + 127) / 128, B, 1024, w.a[0], w.s[0], w.x4, st));
+
+    return SED_OK;
+}
+
 }  // namespace sed
 
 using namespace sed;
@@ -137,24 +162,7 @@ int sed_sednet_forward_g1(const float* const* P, const float* points, const int*
     FwdWs w;
     carve_fwd(A, B, N, k, w);
     const long long fb = 256LL * N;  // batch stride of feats
-
-    // ---- encoder: three EdgeConv blocks (src/SEDNet.py:80-92)
-    // (the first layer's graph depends on the input only: a caller running several networks on the same clouds
-    // computes it once with sed_knn_pn and passes it in)
-    if (!idx1) SED_TRY(knn_pn(points, 6LL * N, B, N, k, normal_metric_W, w.idx, 0, st));
-    SED_TRY(edgeconv(points, 6LL * N, idx1 ? idx1 : w.idx, P[SED_P_ENC_CONV1_W], P[SED_P_ENC_BN1_W], P[SED_P_ENC_BN1_B], B, 6, 64, N,
-                     k, 2, kGnEps, 0.2f, w.feats, fb, w.e, st));
-    SED_TRY(knn_l2(w.feats, fb, B, 64, N, k, w.idx, 0, st));
-    SED_TRY(edgeconv(w.feats, fb, w.idx, P[SED_P_ENC_CONV2_W], P[SED_P_ENC_BN2_W], P[SED_P_ENC_BN2_B], B, 64, 64, N, k,
-                     2, kGnEps, 0.2f, w.feats + 64LL * N, fb, w.e, st));
-    SED_TRY(knn_l2(w.feats + 64LL * N, fb, B, 64, N, k, w.idx, 0, st));
-    SED_TRY(edgeconv(w.feats + 64LL * N, fb, w.idx, P[SED_P_ENC_CONV3_W], P[SED_P_ENC_BN3_W], P[SED_P_ENC_BN3_B], B, 64,
-                     128, N, k, 2, kGnEps, 0.2f, w.feats + 128LL * N, fb, w.e, st));
-
-    // ---- mlp1 + GroupNorm(8) + ReLU + max over N (src/SEDNet.py:95-96); the (B,1024,N) tensor is never written
-    SED_TRY(conv_gn(w.feats, fb, P[SED_P_ENC_MLP1_W], 256, P[SED_P_ENC_MLP1_B], 0, nullptr, nullptr, 0, nullptr, B, 256,
-                    1024, N, 8, P[SED_P_ENC_BNMLP1_W], P[SED_P_ENC_BNMLP1_B], w.a[0], w.s[0], w, w.mm, st));
-    SED_TRY(pool_finalize(w.mm, (N + 127) / 128, B, 1024, w.a[0], w.s[0], w.x4, st));
+    SED_TRY(encoder(P, points, idx1, B, N, k, normal_metric_W, w, st));
 
     // ---- conv1 over cat([x4 repeated, feats]) (src/SEDNet.py:300-303): global half as a per-cloud bias
     SED_TRY(gemv_bias(P[SED_P_CONV1_W], 1280, P[SED_P_CONV1_B], w.x4, B, 1024, 512, w.gbias, st));
@@ -191,6 +199,23 @@ int sed_sednet_forward_g1(const float* const* P, const float* points, const int*
     if (x4_out) SED_CUDA(cudaMemcpyAsync(x4_out, w.x4, (size_t)B * 1024 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     if (feats_out)
         SED_CUDA(cudaMemcpyAsync(feats_out, w.feats, (size_t)B * 256 * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return SED_OK;
+}
+
+int sed_encoder_forward(const float* const* P, const float* points, int B, int N, int k, float normal_metric_W,
+                        float* x4_out, float* feats_out, void* workspace, int64_t workspace_bytes, sed_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!P || !points || !x4_out || !feats_out || !workspace) return SED_ERR_ARG;
+    if (B <= 0 || N < k || k <= 0 || k > 256) return SED_ERR_ARG;
+    for (int i = 0; i <= SED_P_ENC_BNMLP1_B; ++i)
+        if (!P[i]) return SED_ERR_ARG;
+    if (workspace_bytes < sed_sednet_workspace_bytes(B, N, k)) return SED_ERR_ARG;
+    Arena A(workspace, workspace_bytes);
+    FwdWs w;
+    carve_fwd(A, B, N, k, w);
+    SED_TRY(encoder(P, points, nullptr, B, N, k, normal_metric_W, w, st));
+    SED_CUDA(cudaMemcpyAsync(x4_out, w.x4, (size_t)B * 1024 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    SED_CUDA(cudaMemcpyAsync(feats_out, w.feats, (size_t)B * 256 * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return SED_OK;
 }
 

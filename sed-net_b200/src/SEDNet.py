@@ -35,10 +35,26 @@ class DGCNNEncoderGn(nn.Module):
         self.mlp1 = nn.Conv1d(256, 1024, 1)
         self.bnmlp1 = nn.GroupNorm(8, 1024)
 
+        self._ws = None
+
+    @torch.no_grad()
     def forward(self, x):
         """src/SEDNet.py:78-98 (mode 5): (B,6,N) -> x4 (B,1024), x_features (B,256,N)."""
-        raise RuntimeError("DGCNNEncoderGn.forward is fused into SEDNet.forward on this build; "
-                           "call SEDNet.encode(points) for (x4, x_features)")
+        x = _lib.require_cuda(x, name="x")
+        B, Cc, N = x.shape
+        if Cc != 6:
+            raise RuntimeError("DGCNNEncoderGn (mode 5) expects an input of shape (B, 6, N)")
+        dev = x.device
+        table, keep = _lib.param_table(dict(self.named_parameters()), dev, prefix="encoder.", count=13)
+        need = _lib.load().sed_sednet_workspace_bytes(B, N, self.k)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        x4 = torch.empty((B, 1024), dtype=torch.float32, device=dev)
+        feats = torch.empty((B, 256, N), dtype=torch.float32, device=dev)
+        _lib.call("sed_encoder_forward", table, _lib.ptr(x), B, N, self.k, float(self.normal_metric_W), _lib.ptr(x4),
+                  _lib.ptr(feats), _lib.ptr(self._ws), need, _lib.stream())
+        del keep
+        return x4, feats
 
 
 class SEDNet(nn.Module):

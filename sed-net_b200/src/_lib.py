@@ -26,6 +26,7 @@ SIGNATURES = {
                                c_f32p, c_vp, L, c_vp]),
     "sed_sednet_forward_g1": (I, [C.POINTER(C.c_void_p), c_f32p, c_i32p, I, I, I, F, F, I, I, c_f32p, c_f32p, c_f32p,
                                   c_f32p, c_f32p, c_vp, L, c_vp]),
+    "sed_encoder_forward": (I, [C.POINTER(C.c_void_p), c_f32p, I, I, I, F, c_f32p, c_f32p, c_vp, L, c_vp]),
     "sed_edgeconv_workspace_bytes": (L, [I, I, I]),
     "sed_edgeconv_forward": (I, [c_f32p, L, c_i32p, c_f32p, c_f32p, c_f32p, I, I, I, I, I, I, F, F, c_f32p, L, c_vp,
                                  c_vp]),
@@ -113,12 +114,13 @@ def stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def param_table(state, device):
-    """SED_P_COUNT device pointers (ctypes array) + the tensors that must stay alive."""
+def param_table(state, device, prefix="", count=None):
+    """SED_P_COUNT device pointers (ctypes array) + the tensors that must stay alive.  With `prefix`, keys are looked
+    up without it (an encoder module's own parameter names) and only the first `count` entries are filled."""
     keep = []
     arr = (C.c_void_p * len(PARAM_KEYS))()
-    for i, k in enumerate(PARAM_KEYS):
-        t = state[k].detach()
+    for i, k in enumerate(PARAM_KEYS[:count]):
+        t = state[k[len(prefix):]].detach()
         if t.device != device or t.dtype != torch.float32 or not t.is_contiguous():
             t = t.to(device=device, dtype=torch.float32).contiguous()
         keep.append(t)

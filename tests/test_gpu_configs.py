@@ -1,0 +1,213 @@
+"""GPU parity at BASELINE.json's full sizes (configs[2] and configs[3]): the oracle cannot run 32-64 clouds of 10 000
+points in seconds, so these tests use size-independent properties -- FP64 brute force on sampled rows, batch
+invariance (a cloud gives the same result alone and inside the batch), planted partitions recovered exactly, analytic
+surfaces fitted to zero residual -- plus the oracle on ONE cloud of the batch."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+from sednet_b200 import synth
+from util import canon, cylinder_fp64, knn_set_agreement, rel_err, sign_align, t
+
+pytestmark = pytest.mark.gpu
+N = 10000
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from sednet_b200.src import _lib
+    _lib.load()
+    return torch.device("cuda", 0)
+
+
+def _pn_metric_fp64(x6, r, W=1.0):
+    p, n = x6[:3].astype(np.float64), x6[3:].astype(np.float64)
+    pd = ((p - p[:, r:r + 1]) ** 2).sum(0)
+    nd = 2 - 2 * (n * n[:, r:r + 1]).sum(0)
+    return pd * (1 + nd * W)
+
+
+def test_config3_knn_edgeconv_batch32(dev):
+    """configs[2]: batch = 32 x 10 000 points, kNN k = 20 / 64 on the 6-channel (point x normal) and 64-channel (L2)
+    metrics + the EdgeConv encoder."""
+    from sednet_b200.src import PointNet, SEDNet
+    B = 32
+    pts, nrm, lab, typ = synth.make_batch(B, N, seed0=900)
+    x6 = np.concatenate([pts, nrm], 2).transpose(0, 2, 1).copy()                     # (B,6,N)
+    X6 = t(x6).to(dev)
+    rng = np.random.default_rng(0)
+    for k in (20, 64):
+        idx = PointNet.knn_points_normals(X6, k, k, 1.0).cpu().numpy()
+        assert idx.shape == (B, N, k) and idx.min() >= 0 and idx.max() < N
+        for b in (0, 13, 31):
+            for r in rng.choice(N, 24, replace=False):
+                d = _pn_metric_fp64(x6[b], r)
+                dk = d[idx[b, r]]
+                kth = np.partition(d, k - 1)[k - 1]
+                assert dk.max() <= kth * (1 + 1e-5) + 1e-7                            # they ARE the k nearest
+                assert (np.diff(dk) > -1e-6).all()                                    # nearest first
+                assert len(set(idx[b, r])) == k
+        alone = PointNet.knn_points_normals(X6[31:32].contiguous(), k, k, 1.0).cpu().numpy()
+        assert np.array_equal(alone[0], idx[31])                                      # batch invariance, bit-exact
+    xf = rng.normal(size=(B, 64, N)).astype(np.float32)
+    XF = t(xf).to(dev)
+    for k in (20, 64):
+        idx = PointNet.knn(XF, k, k).cpu().numpy()
+        for b in (0, 31):
+            xd = xf[b].astype(np.float64)
+            for r in rng.choice(N, 24, replace=False):
+                d = ((xd - xd[:, r:r + 1]) ** 2).sum(0)
+                kth = np.partition(d, k - 1)[k - 1]
+                assert d[idx[b, r]].max() <= kth * (1 + 1e-5) + 1e-5 and idx[b, r, 0] == r
+        alone = PointNet.knn(XF[7:8].contiguous(), k, k).cpu().numpy()
+        assert np.array_equal(alone[0], idx[7])
+    del XF
+    # EdgeConv encoder over the batch: cloud 31 alone == cloud 31 in the batch; cloud 31 vs the oracle
+    sd = synth.make_state_dict(1, randomize_gn=True)
+    m = SEDNet.SEDNet(embedding=True, emb_size=128, primitives=True, num_primitives=6, mode=5, num_channels=6,
+                      combine_label_prim=True, edge_module=True, late_fusion=True, nn_nb=64)
+    m.load_state_dict({kk: t(v) for kk, v in sd.items()})
+    m = m.to(dev).eval()
+    x4, feats = m.encode(X6)
+    x4a, featsa = m.encode(X6[31:32].contiguous())
+    assert float((feats[31] - featsa[0]).abs().max()) < 1e-6 and float((x4[31] - x4a[0]).abs().max()) < 1e-6
+    assert torch.isfinite(feats).all() and torch.isfinite(x4).all()
+    with torch.no_grad():
+        rx4, rfeats, mid = O.encoder_forward({kk: t(v) for kk, v in sd.items()}, t(x6[31:32]), 64)
+    # Stage-wise parity on the oracle's own intermediates (each layer sees the oracle's input and graph, so FP32 near-ties
+    # of the k-th distance cannot propagate): every EdgeConv block to 2e-4 everywhere, every graph >= 99.9 % of the rows
+    from sednet_b200.src import _lib
+    ws = torch.empty(_lib.load().sed_edgeconv_workspace_bytes(1, N, 128), dtype=torch.uint8, device=dev)
+    layers = ((t(x6[31:32]), "idx1", "conv1.0.weight", "bn1", 6, 64, "x1"), (mid["x1"], "idx2", "conv2.0.weight", "bn2", 64, 64, "x2"),
+              (mid["x2"], "idx3", "conv3.0.weight", "bn3", 64, 128, "x3"))
+    for xin, ik, wk, bk, cin, cout, ok in layers:
+        xin_d = xin.to(dev).contiguous()
+        idx_d = mid[ik].to(torch.int32).to(dev).contiguous()
+        W = t(sd["encoder." + wk]).reshape(cout, 2 * cin).to(dev).contiguous()
+        ga, be = t(sd["encoder." + bk + ".weight"]).to(dev), t(sd["encoder." + bk + ".bias"]).to(dev)
+        y = torch.empty((1, cout, N), device=dev)
+        _lib.call("sed_edgeconv_forward", _lib.ptr(xin_d), cin * N, _lib.ptr(idx_d), _lib.ptr(W), _lib.ptr(ga), _lib.ptr(be),
+                  1, cin, cout, N, 64, 2, 1e-5, 0.2, _lib.ptr(y), cout * N, _lib.ptr(ws), _lib.stream())
+        assert float((y.cpu() - mid[ok]).abs().max()) < 2e-4, ok
+        got_idx = (PointNet.knn_points_normals(xin_d, 64, 64, 1.0) if ik == "idx1" else PointNet.knn(xin_d, 64, 64)).cpu().numpy()
+        ref_idx = mid[ik].numpy()
+        rows, shared = knn_set_agreement(got_idx, ref_idx)
+        assert rows >= 0.998 and shared >= 0.99998, (ik, rows, shared)
+        if ik != "idx1":
+            # every row that differs does so inside the FP32 noise of the reference's own Gram-form distance
+            # (src/PointNet.py:76-78: xx_i + xx_j - 2 x_i.x_j cancels |x|^2 ~ 64 down to d^2 ~ 0.05): in FP64 both lists
+            # are the k nearest up to a few ulp of |x_i|^2 + |x_j|^2
+            xd = xin[0].numpy().astype(np.float64)
+            xx = (xd * xd).sum(0)
+            diff = np.flatnonzero((np.sort(got_idx[0], 1) != np.sort(ref_idx[0], 1)).any(1))
+            for r in diff:
+                d = ((xd - xd[:, r:r + 1]) ** 2).sum(0)
+                kth = np.partition(d, 63)[63]
+                tol = 8 * np.finfo(np.float32).eps * (xx[r] + xx.max())
+                assert d[got_idx[0, r]].max() <= kth + tol and d[ref_idx[0, r]].max() <= kth + tol, (ik, r)
+    # End to end the few rows whose k-th neighbour differs at FP32 rounding change one input of a max, and the later
+    # graphs (built on those features) spread that: the bulk must agree, the affected fraction stays small
+    err = (feats[31].cpu() - rfeats[0]).abs()
+    bad_points = float((err.max(0)[0] > 2e-4).float().mean())
+    assert bad_points < 0.15 and float(err.median()) < 1e-5, (bad_points, float(err.median()), float(err.max()))
+    assert float((x4[31].cpu() - rx4[0]).abs().max()) < 5e-2 and float((x4[31].cpu() - rx4[0]).abs().median()) < 1e-5
+
+
+def test_config4_meanshift_fits_batch64(dev):
+    """configs[3]: batch = 64 x 10 000 points, bandwidth + 50 mean-shift iterations + nms + all four primitive fits
+    and residuals, through the batched C-ABI entry points."""
+    from sednet_b200.src import _lib
+    from sednet_b200.src.primitive_forward import fit_segments_batched
+    B, d, S = 64, 128, 32
+    pts, nrm, lab, typ = synth.make_batch(B, N, seed0=2000, n_patches=12)
+    X = torch.empty((B, N, d), dtype=torch.float32)
+    for b in range(B):
+        X[b] = t(synth.make_embedding(lab[b], d, 0.02, 100 + b))
+    X = X.to(dev)
+    kth = torch.empty((B, N), device=dev)
+    bw = torch.empty(B, device=dev)
+    _lib.call("sed_ms_bandwidth", _lib.ptr(X), B, N, d, 150, 0.003, _lib.ptr(kth), _lib.ptr(bw), _lib.stream())
+    out, tmp = torch.empty_like(X), torch.empty_like(X)
+    _lib.call("sed_ms_shift", _lib.ptr(X), _lib.ptr(bw), B, N, d, 50, 0, 3, _lib.ptr(out), _lib.ptr(tmp), _lib.stream())
+    del tmp
+    labels = torch.empty((B, N), dtype=torch.int64, device=dev)
+    ids = torch.empty((B, S), dtype=torch.int32, device=dev)
+    ncen = torch.empty(B, dtype=torch.int32, device=dev)
+    nlab = torch.empty(B, dtype=torch.int32, device=dev)
+    cen = torch.empty((B, S, d), device=dev)
+    ws = torch.empty(_lib.load().sed_ms_nms_workspace_bytes(B, N), dtype=torch.uint8, device=dev)
+    _lib.call("sed_ms_nms", _lib.ptr(out), _lib.ptr(X), _lib.ptr(bw), B, N, d, S, _lib.ptr(labels), _lib.ptr(ids),
+              _lib.ptr(ncen), _lib.ptr(nlab), _lib.ptr(cen), _lib.ptr(ws), _lib.stream())
+    got = labels.cpu().numpy()
+    for b in range(B):
+        assert (canon(got[b]) == canon(lab[b])).all(), b                              # planted partition, exactly
+        assert int(nlab[b]) == len(np.unique(lab[b]))
+    assert float((torch.linalg.norm(out, dim=2) - 1).abs().max()) < 1e-5              # stays on the unit sphere
+    # the bandwidth of cloud 5 against the oracle (one N x N pass on the CPU)
+    ref_bw = float(O.ms_bandwidth(X[5].cpu(), 10000, 0.015))
+    assert abs(float(bw[5]) - ref_bw) < 1e-4 * ref_bw
+    del out, X
+    # fits of every ground-truth segment of the 64 clouds in one launch
+    st = np.zeros((B, S), np.int32)
+    for b in range(B):
+        for s in range(int(lab[b].max()) + 1):
+            st[b, s] = typ[b][lab[b] == s][0]
+    P, Nn, L, ST = t(pts).to(dev), t(nrm).to(dev), t(lab.astype(np.int64)).to(dev), t(st).to(dev)
+    params, status = fit_segments_batched(P, Nn, L, ST)
+    res = torch.empty((B, S), device=dev)
+    _lib.call("sed_residual_segments", _lib.ptr(P), _lib.ptr(L), _lib.ptr(ST), _lib.ptr(params), _lib.ptr(status), B, N,
+              S, 1, _lib.ptr(res), _lib.stream())
+    params, status, res = params.cpu().numpy(), status.cpu().numpy(), res.cpu().numpy()
+    fitted = status != 1
+    assert fitted.sum() == sum(int(lab[b].max()) + 1 for b in range(B))
+    # exact analytic patches: planes and spheres fit to (guarded-sqrt) residual ~ sqrt(1e-5) floor; all stay small
+    assert np.isfinite(params[fitted]).all()
+    planes_spheres = fitted & ((st == 1) | (st == 5))
+    assert res[planes_spheres].max() < 5e-3, res[planes_spheres].max()
+    for b in (0, 63):                                                                 # the oracle on two of the clouds
+        fits = O.fit_segments(t(pts[b]), t(nrm[b]), lab[b], st[b])
+        for s, v in fits.items():
+            q = params[b, s].astype(np.float64)
+            if v[0] == "plane":
+                ref = np.concatenate([v[1].numpy().ravel(), [float(v[2])]])
+                assert rel_err(q[:4] if q[:3] @ ref[:3] > 0 else -q[:4], ref) < 1e-4
+            elif v[0] == "sphere":
+                assert rel_err(q[:4], np.concatenate([v[1].numpy().ravel(), [float(v[2])]])) < 1e-4
+            elif v[0] == "cone":
+                ref = np.concatenate([v[1].numpy().ravel(), v[2].numpy().ravel(), [float(v[3])]])
+                assert rel_err(q[:7], ref) < 2e-4
+            else:
+                # the reference's FP32 explicit-inverse solve is noisy in the regularised branch (cond ~ 1e6, see
+                # test_fit_batched_vs_oracle_and_edge_cases): axis against the oracle, centre / radius against the FP64
+                # evaluation of the same formulas
+                ax = v[1].numpy().ravel().astype(np.float64)
+                assert abs(abs(q[:3] @ ax) - 1) < 1e-5 and abs(q[6] - float(v[3])) < 2e-2
+                m = lab[b] == s
+                a64, c64, r64 = cylinder_fp64(pts[b][m], nrm[b][m], np.ones(int(m.sum())))
+                assert rel_err(np.concatenate([sign_align(q[:3], a64), q[3:7]]), np.concatenate([a64, c64, [r64]])) < 1e-4
+
+
+def test_encoder_module_forward_matches_fused(dev):
+    """DGCNNEncoderGn.forward(x) -> (x4, x_features) (src/SEDNet.py:78-98) on its own parameters equals the encoder
+    outputs of the fused SEDNet forward, and the oracle."""
+    from sednet_b200.src import SEDNet
+    sd = synth.make_state_dict(0)
+    m = SEDNet.SEDNet(embedding=True, emb_size=128, primitives=True, num_primitives=6, mode=5, num_channels=6,
+                      combine_label_prim=True, edge_module=True, late_fusion=True, nn_nb=32)
+    m.load_state_dict({kk: t(v) for kk, v in sd.items()})
+    m = m.to(dev).eval()
+    pts, nrm, _, _ = synth.make_batch(2, 1500, seed0=77, n_patches=5)
+    x6 = np.concatenate([pts, nrm], 2).transpose(0, 2, 1).copy()
+    x4, feats = m.encoder(t(x6).to(dev))
+    x4b, featsb = m.encode(t(x6).to(dev))
+    assert torch.equal(x4, x4b) and torch.equal(feats, featsb)
+    with torch.no_grad():
+        rx4, rfeats, _ = O.encoder_forward({kk: t(v) for kk, v in sd.items()}, t(x6), 32)
+    err = (feats.cpu() - rfeats).abs()          # robust to a neighbour swapped at an FP32 near-tie (see config3 test)
+    bad_points = float((err.max(1)[0] > 2e-4).float().mean())
+    assert bad_points < 0.1 and float(err.median()) < 1e-5, (bad_points, float(err.median()), float(err.max()))
+    assert float((x4.cpu() - rx4).abs().max()) < 2e-3
