@@ -198,6 +198,38 @@ int sed_fit_segments(const float* points, const float* normals, const float* wei
                      const int* seg_type, int B, int N, int S, int min_pts, float* params, int* status,
                      sed_stream_t stream);
 
+/* ------------------------------------------------------------------ stage 2 (Fitting_patches_and_edges/) */
+
+/* Stage-2 variants of the four fits, Fitting_patches_and_edges/primitive_forward_v2.py:716-891 with
+ * circle_fit_utils.py:11-113, same argument and output layout as sed_fit_segments (type ids SED_PRIM_*; the stage-2
+ * dispatcher's own ids 1 plane / 3 cone / 2 cylinder / 4 sphere, :953-976, are mapped by the caller):
+ *   plane     fit on the int(n * plane_filter_ratio) points nearest to the segment mean (ratio <= 0: no crop)
+ *   sphere    as stage 1
+ *   cylinder  axis from the SVD of the weighted normals (nearest n // 3 points when n > 600), circle by an algebraic
+ *             2-D fit in the plane of the projected points -> [a0 a1 a2 c0 c1 c2 r]
+ *   cone      nearest n // 2 points; apex from the unweighted least squares normals.c = normals.p, axis from the plane
+ *             fit of the points, oriented and snapped by the rules of :868-879 -> [c0 c1 c2 a0 a1 a2 theta]
+ * status: 0 fitted, 1 skipped. */
+int sed_fit_segments_v2(const float* points, const float* normals, const float* weights, const int64_t* labels,
+                        const int* seg_type, int B, int N, int S, int min_pts, double plane_filter_ratio, float* params,
+                        int* status, sed_stream_t stream);
+
+/* pointnet2 three_nn, Fitting_patches_and_edges/pointnet2/_ext_src/src/interpolate_gpu.cu:14-66: for every row of
+ * unknown (B,n,3) the three nearest rows of known (B,m,3): dist2 (B,n,3) squared distances ascending, idx (B,n,3) int32;
+ * equal distances keep the lowest index. */
+int sed_three_nn(const float* unknown, const float* known, int B, int n, int m, float* dist2, int* idx,
+                 sed_stream_t stream);
+
+/* get_edges_between_insts, Fitting_patches_and_edges/proj_2_edge_utils.py:45-60: idx3 (n,3) = three_nn of the cloud on
+ * itself, insts (n) int64 -> out (n) uint8: first (strict: and second) non-self neighbour belongs to another instance. */
+int sed_inst_edges(const int* idx3, const int64_t* insts, int n, int strict, uint8_t* out, sed_stream_t stream);
+
+/* face_face_inter_map, proj_2_edge_utils.py:63-110: mat (30,30) uint8, mat[a][b] = 1 when at least nn_num_thresh first /
+ * second neighbours of instance a's points belong to instance b; an instance of primitive_ids (n_ids, int64) without
+ * any neighbour gets the instance of the point nearest to its first point. */
+int sed_face_face_map(const float* points, const int64_t* insts, const int* idx3, const int64_t* primitive_ids, int n_ids,
+                      int n, int nn_num_thresh, uint8_t* mat, sed_stream_t stream);
+
 /* LeastSquares.lstsq(A, Y, lamb) src/fitting_utils.py:36-65 for one (m,3) system: x (3); status 0 full rank (QR
  * branch), 2 regularised branch (best_lambda :68-85). */
 int sed_lstsq3(const float* A, const float* Y, int m, float* x, int* status, sed_stream_t stream);

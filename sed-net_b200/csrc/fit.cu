@@ -110,7 +110,10 @@ struct FitParams {
 
 struct SegIter {
     const float* pts; const float* nrm; const float* wts; const long long* labels; int N, s;
-    __device__ __forceinline__ bool member(int i) const { return !labels || labels[i] == (long long)s; }
+    const unsigned char* mask = nullptr;   // stage-2 centre crop: members with mask[i] == 0 are left out
+    __device__ __forceinline__ bool member(int i) const {
+        return (!labels || labels[i] == (long long)s) && (!mask || mask[i]);
+    }
     __device__ __forceinline__ double w(int i) const { return wts ? (double)wts[i] : 1.0; }
     __device__ __forceinline__ void p(int i, double v[3]) const {
         v[0] = pts[3 * i]; v[1] = pts[3 * i + 1]; v[2] = pts[3 * i + 2];
@@ -304,6 +307,269 @@ __global__ void __launch_bounds__(FIT_THREADS) fit_segments_kernel(FitParams p) 
     if (threadIdx.x == 0) *status = st;
 }
 
+// ------------------------------------------------------------------------------------------------ stage-2 fits
+// Fitting_patches_and_edges/primitive_forward_v2.py:716-891 (+ circle_fit_utils.py:11-113): the same moment-matrix
+// fits on a CENTRE CROP of the segment -- the m points nearest to the segment's mean, m = int(n * filter_ratio)
+// (plane), n // 3 when n > 600 (cylinder), n // 2 (cone) -- with the cylinder's circle found by an algebraic 2-D fit
+// in the plane of the projected points and the cone's apex / axis by the stage-2 rules.  The crop is an exact
+// selection: a 4 x 8-bit radix select over the FP32 squared distances (shared-memory histogram), ties at the m-th
+// distance taken in index order.
+struct FitParamsV2 {
+    const float* pts; const float* nrm; const float* wts; const long long* labels; const int* seg_type;
+    int N, S, min_pts;
+    double plane_ratio;
+    unsigned char* mask;   // (B,N) scratch
+    float* params; int* status;
+};
+
+struct CropShared {
+    unsigned int hist[256];
+    unsigned int prefix, less, want;
+    unsigned long long first;
+};
+
+__device__ __forceinline__ float crop_d2(const SegIter& it, int i, float cx, float cy, float cz) {
+    // (points - center).pow(2).sum(-1) in FP32 (:723-724), no FMA contraction
+    const float dx = __fsub_rn(it.pts[3 * i], cx), dy = __fsub_rn(it.pts[3 * i + 1], cy), dz = __fsub_rn(it.pts[3 * i + 2], cz);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+// Marks in `mask` the m members of the segment nearest to its (unweighted) mean; returns in first_idx the nearest one
+// (points[0] of the reference's sorted crop).  All threads of the CTA call.
+__device__ void crop_nearest(const SegIter& it, int n, int m, unsigned char* mask, Shared& sh, CropShared& cs, int& first_idx) {
+    double c[3] = {0, 0, 0};
+    for (int i = threadIdx.x; i < it.N; i += FIT_THREADS) {
+        if (!it.member(i)) continue;
+        c[0] += it.pts[3 * i]; c[1] += it.pts[3 * i + 1]; c[2] += it.pts[3 * i + 2];
+    }
+    reduce<3>(c, sh);
+    const float cx = (float)(c[0] / n), cy = (float)(c[1] / n), cz = (float)(c[2] / n);
+    if (threadIdx.x == 0) { cs.prefix = 0; cs.want = (unsigned)m; cs.less = 0; cs.first = ~0ull; }
+    __syncthreads();
+    unsigned long long best = ~0ull;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += FIT_THREADS) cs.hist[i] = 0;
+        __syncthreads();
+        const unsigned prefix = cs.prefix;
+        for (int i = threadIdx.x; i < it.N; i += FIT_THREADS) {
+            if (!it.member(i)) continue;
+            const unsigned key = __float_as_uint(crop_d2(it, i, cx, cy, cz));   // d2 >= 0: integer order = float order
+            if (pass == 0) {
+                const unsigned long long e = ((unsigned long long)key << 32) | (unsigned)i;
+                best = e < best ? e : best;
+            }
+            if (pass == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&cs.hist[(key >> shift) & 255u], 1u);
+        }
+        if (pass == 0) atomicMin(&cs.first, best);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned want = cs.want, bin = 0;
+            for (; bin < 256; ++bin) {
+                if (cs.hist[bin] >= want) break;
+                want -= cs.hist[bin];
+            }
+            bin = bin > 255u ? 255u : bin;
+            cs.prefix = (prefix << 8) | bin;
+            cs.want = want;            // rank still to resolve inside the chosen bin
+        }
+        __syncthreads();
+    }
+    const unsigned T = cs.prefix;      // bit pattern of the m-th smallest distance
+    const unsigned quota = cs.want;    // how many of the entries equal to T belong to the crop
+    unsigned ties_l = 0;
+    for (int i = threadIdx.x; i < it.N; i += FIT_THREADS) {
+        if (!it.member(i)) continue;
+        const unsigned key = __float_as_uint(crop_d2(it, i, cx, cy, cz));
+        mask[i] = key <= T ? 1 : 0;
+        ties_l += key == T ? 1u : 0u;
+    }
+    double tt[1] = {(double)ties_l};
+    reduce<1>(tt, sh);
+    if ((unsigned)tt[0] > quota) {     // rare: more equal distances than the crop takes -> the first `quota` in index order
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned seen = 0;
+            for (int i = 0; i < it.N; ++i) {
+                if (!it.member(i)) continue;
+                if (__float_as_uint(crop_d2(it, i, cx, cy, cz)) == T) { if (seen >= quota) mask[i] = 0; ++seen; }
+            }
+        }
+    }
+    __syncthreads();
+    first_idx = (int)(cs.first & 0xffffffffull);
+}
+
+// a^-1 b for a symmetric 3x3 system through its eigen-decomposition, directions below sigma_max * rows * eps dropped
+// (the minimum-norm least-squares solution of np.linalg.lstsq / torch.linalg.lstsq on the normal equations)
+__device__ void solve_sym3(const Sym3& G, const double g[3], int nrows, double x[3]) {
+    double mu[3], V[3][3];
+    eig3(G, mu, V);
+    const double rt = (double)max(nrows, 3) * kEps32;
+    const double tol = mu[0] * rt * rt;   // on eigenvalues = singular values squared
+    x[0] = x[1] = x[2] = 0.0;
+    for (int i = 0; i < 3; ++i) {
+        if (!(mu[i] > tol)) continue;
+        const double y = (V[0][i] * g[0] + V[1][i] * g[1] + V[2][i] * g[2]) / mu[i];
+        x[0] += V[0][i] * y; x[1] += V[1][i] * y; x[2] += V[2][i] * y;
+    }
+}
+
+// Rodrigues rotation taking unit vector n0 to n1 applied to v (circle_fit_utils.py:11-28)
+__device__ void rodrigues(const double n0[3], const double n1[3], const double v[3], double out[3]) {
+    double k[3] = {n0[1] * n1[2] - n0[2] * n1[1], n0[2] * n1[0] - n0[0] * n1[2], n0[0] * n1[1] - n0[1] * n1[0]};
+    const double kn = sqrt(k[0] * k[0] + k[1] * k[1] + k[2] * k[2]);
+    k[0] /= kn; k[1] /= kn; k[2] /= kn;                       // n0 parallel to n1: 0/0 = NaN, as in the reference
+    const double ct = fmin(fmax(n0[0] * n1[0] + n0[1] * n1[1] + n0[2] * n1[2], -1.0), 1.0);
+    const double st = sin(acos(ct));
+    const double kv = k[0] * v[0] + k[1] * v[1] + k[2] * v[2];
+    const double cr[3] = {k[1] * v[2] - k[2] * v[1], k[2] * v[0] - k[0] * v[2], k[0] * v[1] - k[1] * v[0]};
+    for (int i = 0; i < 3; ++i) out[i] = v[i] * ct + cr[i] * st + k[i] * kv * (1.0 - ct);
+}
+
+__global__ void __launch_bounds__(FIT_THREADS) fit_segments_v2_kernel(FitParamsV2 p) {
+    __shared__ Shared sh;
+    __shared__ CropShared cs;
+    const int s = blockIdx.x, b = blockIdx.y;
+    const long long base = (long long)b * p.N;
+    SegIter it{p.pts + base * 3, p.nrm ? p.nrm + base * 3 : nullptr, p.wts ? p.wts + base : nullptr,
+               p.labels ? p.labels + base : nullptr, p.N, s};
+    unsigned char* mask = p.mask + base;
+    float* out = p.params + ((long long)b * p.S + s) * SED_FIT_PARAMS;
+    int* status = p.status + (long long)b * p.S + s;
+    const int type = p.seg_type[(long long)b * p.S + s];
+
+    double cnt[1] = {0};
+    for (int i = threadIdx.x; i < it.N; i += FIT_THREADS) cnt[0] += it.member(i) ? 1.0 : 0.0;
+    reduce<1>(cnt, sh);
+    const int n = (int)cnt[0];
+    const bool analytic = type == SED_PRIM_PLANE || type == SED_PRIM_CONE || type == SED_PRIM_CYLINDER || type == SED_PRIM_SPHERE;
+    double res[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int st = 1;
+    if (analytic && n >= p.min_pts && n > 0 && (it.nrm || type == SED_PRIM_PLANE || type == SED_PRIM_SPHERE)) {
+        int m = n, first = 0;
+        if (type == SED_PRIM_PLANE && p.plane_ratio > 0.0) m = (int)((double)n * p.plane_ratio);   // :722-725
+        if (type == SED_PRIM_CYLINDER && n > 600) m = n / 3;                                          // :830-835
+        if (type == SED_PRIM_CONE) m = n / 2;                                                         // :854-856
+        m = max(m, 1);
+        if (m < n || type == SED_PRIM_CONE) {
+            crop_nearest(it, n, m, mask, sh, cs, first);
+            it.mask = mask;
+        }
+        if (type == SED_PRIM_PLANE) {
+            double a[3], d;
+            plane_fit(it, false, sh, a, d);
+            res[0] = a[0]; res[1] = a[1]; res[2] = a[2]; res[3] = d;
+            st = 0;
+        } else if (type == SED_PRIM_SPHERE) {      // :772-796, the stage-1 algebra
+            double c[3], r;
+            st = sphere_fit(it, nullptr, n, sh, c, r);
+            res[0] = c[0]; res[1] = c[1]; res[2] = c[2]; res[3] = r;
+        } else if (type == SED_PRIM_CYLINDER) {
+            double acc[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = threadIdx.x; i < it.N; i += FIT_THREADS) {
+                if (!it.member(i)) continue;
+                double nn[3]; it.n(i, nn);
+                const double w = it.w(i);
+                add_outer(acc, w * w, nn);
+            }
+            reduce<6>(acc, sh);
+            double a[3], ev[3];
+            smallest_vec(sym(acc), a, ev);
+            const double an = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]) + kEps32;
+            a[0] /= an; a[1] /= an; a[2] /= an;
+            // circle_segmentation (circle_fit_utils.py:80-113) of prj = p - (p.a) a
+            auto prj = [&](int i, double v[3]) {
+                it.p(i, v);
+                const double t = v[0] * a[0] + v[1] * a[1] + v[2] * a[2];
+                v[0] -= t * a[0]; v[1] -= t * a[1]; v[2] -= t * a[2];
+            };
+            double mm[4] = {0, 0, 0, 0};
+            for (int i = threadIdx.x; i < it.N; i += FIT_THREADS) {
+                if (!it.member(i)) continue;
+                double v[3]; prj(i, v);
+                mm[0] += 1.0; mm[1] += v[0]; mm[2] += v[1]; mm[3] += v[2];
+            }
+            reduce<4>(mm, sh);
+            const double mean[3] = {mm[1] / mm[0], mm[2] / mm[0], mm[3] / mm[0]};
+            double cov[6] = {0, 0, 0, 0, 0, 0};
+            for (int i = threadIdx.x; i < it.N; i += FIT_THREADS) {
+                if (!it.member(i)) continue;
+                double v[3]; prj(i, v);
+                const double dv[3] = {v[0] - mean[0], v[1] - mean[1], v[2] - mean[2]};
+                add_outer(cov, 1.0, dv);
+            }
+            reduce<6>(cov, sh);
+            double nv[3];
+            smallest_vec(sym(cov), nv, ev);
+            const double z[3] = {0.0, 0.0, 1.0};
+            // [x y 1] c = x^2 + y^2 in the rotated frame
+            double q[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = threadIdx.x; i < it.N; i += FIT_THREADS) {
+                if (!it.member(i)) continue;
+                double v[3], r3[3]; prj(i, v);
+                v[0] -= mean[0]; v[1] -= mean[1]; v[2] -= mean[2];
+                rodrigues(nv, z, v, r3);
+                const double x = r3[0], y = r3[1], bb = x * x + y * y;
+                q[0] += x * x; q[1] += x * y; q[2] += x; q[3] += y * y; q[4] += y; q[5] += 1.0;
+                q[6] += x * bb; q[7] += y * bb; q[8] += bb;
+            }
+            reduce<9>(q, sh);
+            double cc[3];
+            solve_sym3(sym(q), q + 6, m, cc);
+            const double xc = cc[0] / 2, yc = cc[1] / 2;
+            const double r = sqrt(cc[2] + xc * xc + yc * yc);
+            const double c2[3] = {xc, yc, 0.0};
+            double C[3];
+            rodrigues(z, nv, c2, C);
+            res[0] = a[0]; res[1] = a[1]; res[2] = a[2];
+            res[3] = C[0] + mean[0]; res[4] = C[1] + mean[1]; res[5] = C[2] + mean[2]; res[6] = r;
+            st = 0;
+        } else {   // cone :851-891
+            double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = threadIdx.x; i < it.N; i += FIT_THREADS) {
+                if (!it.member(i)) continue;
+                double nn[3], v[3]; it.n(i, nn); it.p(i, v);
+                add_outer(*reinterpret_cast<double(*)[6]>(acc), 1.0, nn);
+                const double y = nn[0] * v[0] + nn[1] * v[1] + nn[2] * v[2];
+                acc[6] += y * nn[0]; acc[7] += y * nn[1]; acc[8] += y * nn[2];
+            }
+            reduce<9>(acc, sh);
+            double c[3];
+            solve_sym3(sym(acc), acc + 6, m, c);                 // torch.lstsq(Y, A=normals) (:862)
+            double a[3], dummy;
+            plane_fit(it, false, sh, a, dummy);                  // fit_plane_torch(points, ..., nofilter=True) (:866)
+            double p0[3]; it.p(first, p0);
+            if ((c[0] - p0[0]) * a[0] + (c[1] - p0[1]) * a[1] + (c[2] - p0[2]) * a[2] < 0.0) { a[0] = -a[0]; a[1] = -a[1]; a[2] = -a[2]; }
+            // FP32 compares of the reference (:873-879)
+            for (int i = 0; i < 3; ++i) {
+                if (fabsf((float)a[i]) >= 0.98f) {
+                    const double sg = a[i] > 0 ? 1.0 : -1.0;
+                    a[0] = a[1] = a[2] = 0.0;
+                    a[i] = sg;
+                }
+                if (fabsf((float)c[i]) <= 0.1f) c[i] = 0.0;
+            }
+            double th[2] = {0, 0};
+            for (int i = threadIdx.x; i < it.N; i += FIT_THREADS) {
+                if (!it.member(i)) continue;
+                double v[3]; it.p(i, v);
+                v[0] -= c[0]; v[1] -= c[1]; v[2] -= c[2];
+                const double nv = fmax(sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]), 1e-12);
+                const double dt = fmin(fabs((v[0] * a[0] + v[1] * a[1] + v[2] * a[2]) / nv), 0.999);
+                th[0] += it.w(i) * acos(dt); th[1] += it.w(i);
+            }
+            reduce<2>(th, sh);
+            double theta = th[0] / (th[1] + kEps32);
+            theta = fmin(fmax(theta, 1e-3), 3.142 / 2 - 1e-3);
+            res[0] = c[0]; res[1] = c[1]; res[2] = c[2]; res[3] = a[0]; res[4] = a[1]; res[5] = a[2]; res[6] = theta;
+            st = 0;
+        }
+    }
+    if (threadIdx.x < SED_FIT_PARAMS) out[threadIdx.x] = (float)res[threadIdx.x];
+    if (threadIdx.x == 0) *status = st;
+}
+
 // LeastSquares.lstsq(A, Y) for one (m x 3) system (src/fitting_utils.py:36-65) and the right singular system of an
 // (m x 3) matrix (customsvd forward, src/fitting_utils.py:420-455: S descending, V columns).  Single CTA.
 __global__ void __launch_bounds__(FIT_THREADS) lstsq3_kernel(const float* __restrict__ A, const float* __restrict__ Y, int m,
@@ -470,6 +736,23 @@ int sed_fit_segments(const float* points, const float* normals, const float* wei
     fit_segments_kernel<<<dim3(S, B), FIT_THREADS, 0, (cudaStream_t)stream>>>(p);
     SED_CHECK_LAUNCH();
     return SED_OK;
+}
+
+int sed_fit_segments_v2(const float* points, const float* normals, const float* weights, const int64_t* labels,
+                        const int* seg_type, int B, int N, int S, int min_pts, double plane_filter_ratio, float* params,
+                        int* status, sed_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!points || !seg_type || !params || !status || B <= 0 || N <= 0 || S <= 0 || !(plane_filter_ratio <= 1.0)) return SED_ERR_ARG;
+    ensure_pool_config();
+    unsigned char* mask = nullptr;
+    SED_CUDA(cudaMallocAsync((void**)&mask, (size_t)B * N, st));
+    FitParamsV2 p{points, normals, weights, (const long long*)labels, seg_type, N, S, min_pts, plane_filter_ratio, mask,
+                  params, status};
+    fit_segments_v2_kernel<<<dim3(S, B), FIT_THREADS, 0, st>>>(p);
+    const cudaError_t e = cudaGetLastError();
+    ++g_sed_launches;
+    cudaFreeAsync(mask, st);
+    return e == cudaSuccess ? SED_OK : SED_ERR_CUDA_BASE - (int)e;
 }
 
 int sed_lstsq3(const float* A, const float* Y, int m, float* x, int* status, sed_stream_t stream) {

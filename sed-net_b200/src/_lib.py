@@ -37,6 +37,10 @@ SIGNATURES = {
     "sed_ms_nms": (I, [c_f32p, c_f32p, c_f32p, I, I, I, I, c_i64p, c_i32p, c_i32p, c_i32p, c_f32p, c_vp, c_vp]),
     "sed_one_hot": (I, [c_i64p, I, I, c_f32p, c_vp]),
     "sed_fit_segments": (I, [c_f32p, c_f32p, c_f32p, c_i64p, c_i32p, I, I, I, I, c_f32p, c_i32p, c_vp]),
+    "sed_fit_segments_v2": (I, [c_f32p, c_f32p, c_f32p, c_i64p, c_i32p, I, I, I, I, D, c_f32p, c_i32p, c_vp]),
+    "sed_three_nn": (I, [c_f32p, c_f32p, I, I, I, c_f32p, c_i32p, c_vp]),
+    "sed_inst_edges": (I, [c_i32p, c_i64p, I, I, c_vp, c_vp]),
+    "sed_face_face_map": (I, [c_f32p, c_i64p, c_i32p, c_i64p, I, I, I, c_vp, c_vp]),
     "sed_lstsq3": (I, [c_f32p, c_f32p, I, c_f32p, c_i32p, c_vp]),
     "sed_svd3": (I, [c_f32p, I, c_f32p, c_f32p, c_vp]),
     "sed_residual_segments": (I, [c_f32p, c_i64p, c_i32p, c_f32p, c_i32p, I, I, I, I, c_f32p, c_vp]),

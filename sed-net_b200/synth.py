@@ -133,6 +133,22 @@ def make_batch(batch, n_points=10000, seed0=1234, **kw):
     return tuple(np.stack([c[i] for c in cl]) for i in range(4))
 
 
+def make_touching_instances(seed, n):
+    """Instances that touch (stage-2 adjacency maps): a wavy sheet cut into Voronoi cells of 7 random sites (labels 0-6)
+    plus one isolated blob (label 7: the 'lonely instance' branch of face_face_inter_map).  Returns points (n,3) f32,
+    labels (n,) i64."""
+    rng = np.random.default_rng(seed)
+    uv = rng.uniform(-1, 1, (n - 200, 2))
+    sheet = np.stack([uv[:, 0], uv[:, 1], 0.2 * np.sin(3 * uv[:, 0]) * np.cos(2 * uv[:, 1])], 1)
+    sites = rng.uniform(-1, 1, (7, 2))
+    lab = np.argmin(((uv[:, None] - sites[None]) ** 2).sum(-1), 1)
+    blob = np.array([3.0, 3.0, 3.0]) + 0.05 * rng.normal(size=(200, 3))
+    pts = np.concatenate([sheet, blob]).astype(np.float32)
+    lab = np.concatenate([lab, np.full(200, 7)]).astype(np.int64)
+    perm = rng.permutation(n)
+    return pts[perm], lab[perm]
+
+
 def make_embedding(labels, dim=128, sigma=0.01, seed=0):
     """Unit-norm embedding with one well separated mode per label:
     normalize(centroid[label] + sigma * randn)."""
