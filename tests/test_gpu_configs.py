@@ -211,3 +211,30 @@ def test_encoder_module_forward_matches_fused(dev):
     bad_points = float((err.max(1)[0] > 2e-4).float().mean())
     assert bad_points < 0.1 and float(err.median()) < 1e-5, (bad_points, float(err.median()), float(err.max()))
     assert float((x4.cpu() - rx4).abs().max()) < 2e-3
+
+
+def test_tta_batched_matches_sequential_oracle(dev):
+    """the driver's test-time-augmentation modes (generate_predictions_aug.py:238-362) as single batched
+    forwards against the oracle's sequential B = 1 forwards."""
+    import oracle_tta as OT
+    from sednet_b200 import tta
+    from sednet_b200.src import SEDNet
+    sd = synth.make_state_dict(2, randomize_gn=True)
+    k, n, drop = 24, 1200, 240
+    m = SEDNet.SEDNet(embedding=True, emb_size=128, primitives=True, num_primitives=6, mode=5, num_channels=6,
+                      combine_label_prim=True, edge_module=True, late_fusion=True, nn_nb=k)
+    m.load_state_dict({kk: t(v) for kk, v in sd.items()})
+    m = m.to(dev).eval()
+    pts, nrm, _, _, _ = synth.make_cloud(808, n, n_patches=5)
+    P, Nn = t(pts)[None], t(nrm)[None]
+    sdt = {kk: t(v) for kk, v in sd.items()}
+    with torch.no_grad():
+        refs = (OT.multi_vote(sdt, P, Nn, k), OT.fold5drop(sdt, P, Nn, k, drop), OT.fold5drop_multi_vote(sdt, P, Nn, k, drop))
+    gots = (tta.multi_vote(m, P.to(dev), Nn.to(dev)), tta.fold5drop(m, P.to(dev), Nn.to(dev), drop),
+            tta.fold5drop_multi_vote(m, P.to(dev), Nn.to(dev), drop))
+    for name, got, ref in zip(("multi_vote", "fold5drop", "both"), gots, refs):
+        assert got.shape == ref.shape == (1, 6, n)
+        err = (got.cpu() - ref).abs()
+        # sums of up to 12 log-probabilities; a near-tie neighbour swap perturbs isolated points (see config3 test)
+        assert float(err.median()) < 1e-5 and float((err.max(1)[0] > 1e-3).float().mean()) < 0.02, (name, float(err.max()))
+        assert float((got.argmax(1).cpu() == ref.argmax(1)).float().mean()) > 0.995, name
