@@ -132,32 +132,49 @@ pw_tc_kernel(const __grid_constant__ CUtensorMap map_wh, const __grid_constant__
         const int chunk = lane & 15;                             // 8 consecutive points
         const int pt = n0 + chunk * 8;
         const bool vec_ok = ((p.ldx & 3) == 0) && (pt + 7 < p.N) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0);
+        // raw activations of one K chunk: 4 channel rows x 8 points per thread.  The loads of chunk kc + 1 are issued
+        // before chunk kc is converted, so their latency hides behind the conversion and the wait for a free stage.
+        auto fetch = [&](int kc, float (&r)[4][8]) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int c = kc * PT_KC + pw * 8 + t * 2 + (lane >> 4);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r[t][e] = 0.f;
+                if (c < p.Cin) {
+                    const float* src = X + (long long)c * p.ldx + pt;
+                    if (vec_ok) {
+                        const float4 u0 = __ldg(reinterpret_cast<const float4*>(src));
+                        const float4 u1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                        r[t][0] = u0.x; r[t][1] = u0.y; r[t][2] = u0.z; r[t][3] = u0.w;
+                        r[t][4] = u1.x; r[t][5] = u1.y; r[t][6] = u1.z; r[t][7] = u1.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) if (pt + e < p.N) r[t][e] = __ldg(src + e);
+                    }
+                }
+            }
+        };
+        float nxt[4][8];
+        fetch(0, nxt);
         for (int kc = 0; kc < nk; ++kc) {
             const int s = kc % PT_STAGES;
+            float cur[4][8];
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) cur[t][e] = nxt[t][e];
+            if (kc + 1 < nk) fetch(kc + 1, nxt);
             if (kc >= PT_STAGES) mbar_wait(bar_empty + 8 * s, ((kc / PT_STAGES) - 1) & 1);
             const uint32_t a_hi = stage_addr + s * PT_STAGE, a_lo = a_hi + PT_A_PART;
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
                 const int cl = pw * 8 + t * 2 + (lane >> 4);     // channel within the chunk = row of the image
                 const int c = kc * PT_KC + cl;
-                float v[8];
+                float (&v)[8] = cur[t];
+                if (c < p.Cin && ia) {
+                    const float av = __ldg(ia + c), sv = __ldg(is + c);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                if (c < p.Cin) {
-                    const float* src = X + (long long)c * p.ldx + pt;
-                    if (vec_ok) {
-                        const float4 u0 = __ldg(reinterpret_cast<const float4*>(src));
-                        const float4 u1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                        v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w; v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) if (pt + e < p.N) v[e] = __ldg(src + e);
-                    }
-                    if (ia) {
-                        const float av = __ldg(ia + c), sv = __ldg(is + c);
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = (pt + e < p.N) ? pt_act(fmaf(av, v[e], sv), p.in_act) : 0.f;
-                    }
+                    for (int e = 0; e < 8; ++e) v[e] = (pt + e < p.N) ? pt_act(fmaf(av, v[e], sv), p.in_act) : 0.f;
                 }
                 uint32_t hi[4], lo[4];
 #pragma unroll
