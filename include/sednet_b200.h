@@ -282,6 +282,16 @@ int sed_pipeline_run_host(sed_pipeline_t* p, const float* points_host, const flo
  * handle; used for the device-resident throughput number.  sed_pipeline_device_ptr returns the named buffer. */
 int sed_pipeline_run_device(sed_pipeline_t* p, const float* points_dev, const float* normals_dev, int B,
                             double quantile, int iterations, int prec_mode, sed_stream_t stream);
+/* The two halves of sed_pipeline_run_device, for a driver that post-processes the embedding in between (the
+ * reference inserts hpnet_process there, generate_predictions_aug.py:371-380):
+ *   run_forward  pack the input, first-layer graph, both networks, type argmax, X = normalised embedding (B,N,128)
+ *                (device buffers "X", "embedding", "log_prob", "type_log_prob", "pred_type" of the handle);
+ *   run_cluster  guarded mean-shift of the handle's X (which the caller may have rewritten), per-segment type vote
+ *                from pred_type, fits, residuals.  Host sync per guard try. */
+int sed_pipeline_run_forward(sed_pipeline_t* p, const float* points_dev, const float* normals_dev, int B,
+                             sed_stream_t stream);
+int sed_pipeline_run_cluster(sed_pipeline_t* p, const float* points_dev, const float* normals_dev, int B, double quantile,
+                             int iterations, int prec_mode, sed_stream_t stream);
 void* sed_pipeline_device_ptr(sed_pipeline_t* p, const char* name);
 /* device time (ms, CUDA events on the run's stream) of the stages of the last run: first-layer graph (shared by the
  * two networks), both forwards (type net on an internal side stream, concurrently with the instance net) +

@@ -194,10 +194,15 @@ static int pipe_mean_shift(sed_pipeline* p, int b0, int nb, double quantile, int
 
 int sed_pipeline_run_device(sed_pipeline_t* p, const float* points_dev, const float* normals_dev, int B, double quantile,
                             int iterations, int prec_mode, sed_stream_t stream) {
+    SED_TRY(sed_pipeline_run_forward(p, points_dev, normals_dev, B, stream));
+    return sed_pipeline_run_cluster(p, points_dev, normals_dev, B, quantile, iterations, prec_mode, stream);
+}
+
+int sed_pipeline_run_forward(sed_pipeline_t* p, const float* points_dev, const float* normals_dev, int B,
+                             sed_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!p || !points_dev || !normals_dev || B <= 0 || B > p->max_B || !p->have_weights) return SED_ERR_ARG;
     const int N = p->N, S = p->S;
-    p->retries = 0;
     SED_CUDA(cudaEventRecord(p->ev[0], st));
     pack_input_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(points_dev, normals_dev, N, p->inp);
     SED_CHECK_LAUNCH();
@@ -218,6 +223,15 @@ int sed_pipeline_run_device(sed_pipeline_t* p, const float* points_dev, const fl
     SED_TRY(sed_normalize_transpose(p->emb, B, p->E, N, p->X, st));
     SED_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
     SED_CUDA(cudaEventRecord(p->ev[2], st));
+    return SED_OK;
+}
+
+int sed_pipeline_run_cluster(sed_pipeline_t* p, const float* points_dev, const float* normals_dev, int B, double quantile,
+                             int iterations, int prec_mode, sed_stream_t stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!p || !points_dev || !normals_dev || B <= 0 || B > p->max_B) return SED_ERR_ARG;
+    const int N = p->N, S = p->S;
+    p->retries = 0;
     // guarded mean-shift: re-run a cloud with quantile * 1.2 while it has more than 49 labels
     SED_TRY(pipe_mean_shift(p, 0, B, (double)quantile, iterations, prec_mode, true, st));
     SED_CUDA(cudaMemcpyAsync(p->h_counts, p->n_labels, B * sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -79,6 +79,24 @@ class Pipeline:
         _lib.call("sed_pipeline_run_device", self._h, _lib.ptr(points), _lib.ptr(normals), B, float(quantile),
                   int(iterations), int(prec_mode), _lib.stream())
 
+    def run_forward(self, points, normals):
+        """First half of run_device: both networks; leaves X = normalised embedding (B,N,128) in the handle
+        (``device_tensor_view("X")`` is writable: a driver may post-process the embedding before clustering)."""
+        points = _lib.require_cuda(points, name="points")
+        normals = _lib.require_cuda(normals, name="normals")
+        B = points.shape[0]
+        assert points.shape == (B, self.N, 3) and B <= self.B
+        _lib.call("sed_pipeline_run_forward", self._h, _lib.ptr(points), _lib.ptr(normals), B, _lib.stream())
+
+    def run_cluster(self, points, normals, quantile=0.015, iterations=50, prec_mode=0):
+        """Second half: guarded mean-shift of the handle's X, type vote, fits, residuals (results on the device)."""
+        points = _lib.require_cuda(points, name="points")
+        normals = _lib.require_cuda(normals, name="normals")
+        B = points.shape[0]
+        assert points.shape == (B, self.N, 3) and B <= self.B
+        _lib.call("sed_pipeline_run_cluster", self._h, _lib.ptr(points), _lib.ptr(normals), B, float(quantile),
+                  int(iterations), int(prec_mode), _lib.stream())
+
     STAGES = ("graph1", "forwards", "bandwidth", "shift", "nms", "fit")
 
     def stage_ms(self):

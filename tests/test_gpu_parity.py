@@ -456,3 +456,38 @@ def test_pipeline_split_precision_mode(dev):
         assert np.array_equal(out["pred_type"][b].numpy(), ref0["pred_type"][b].numpy())
         assert abs(float(out["bw"][b]) - float(ref0["bw"][b])) == 0.0
     pipe.close()
+
+
+def test_pipeline_guard_loop_with_planted_embeddings(dev):
+    """The guard loop of the driver (generate_predictions_aug.py:25-35: quantile *= 1.2 while a cloud has more than 49
+    labels) through the two-phase pipeline: run_forward, then the handle's X is replaced by planted embeddings -- 52
+    clusters for cloud 0 (one retry: K = 180 exceeds the 153-point clusters and everything merges), 8 for cloud 1 (no
+    retry) -- and run_cluster must reproduce the oracle's guarded labels, bandwidths and label counts."""
+    from sednet_b200.pipeline import Pipeline
+    B, N, k, it = 2, 8000, 32, 10
+    pts, nrm, _, _ = synth.make_batch(B, N, seed0=77, n_patches=6)
+    rng = np.random.default_rng(12)
+    labs = [rng.permutation(np.arange(N) % 52), rng.permutation(np.arange(N) % 8)]
+    X = torch.stack([t(synth.make_embedding(labs[b], 128, 0.01, 40 + b)) for b in range(B)])
+    pipe = Pipeline(B, N, k, max_segments=64)
+    pipe.set_weights(synth.make_state_dict(0), synth.make_state_dict(1, randomize_gn=True))
+    P, Nn = t(pts).to(dev), t(nrm).to(dev)
+    pipe.run_forward(P, Nn)
+    pipe.device_tensor_view("X").copy_(X.to(dev))
+    pipe.run_cluster(P, Nn, 0.015, it, 0)
+    _, retries = pipe.stage_ms()
+    assert retries == 1
+    labels, nlab, bw = pipe.device_tensor("labels").cpu().numpy(), pipe.device_tensor("n_labels").cpu().numpy(), pipe.device_tensor("bw").cpu().numpy()
+    for b in range(B):
+        with torch.no_grad():
+            _, rbw, rlab = O.guard_mean_shift(X[b], 0.015, it)
+        assert (canon(labels[b]) == canon(rlab.numpy())).all(), b
+        assert int(nlab[b]) == len(np.unique(rlab.numpy())) and abs(float(bw[b]) - float(rbw)) < 1e-4 * float(rbw)
+    assert int(nlab[0]) <= 49 and int(nlab[1]) == 8
+    # the same second phase in the bench's tensor-core mode gives the same partition
+    pipe.device_tensor_view("X").copy_(X.to(dev))
+    pipe.run_cluster(P, Nn, 0.015, it, 3)
+    labels3 = pipe.device_tensor("labels").cpu().numpy()
+    for b in range(B):
+        assert (canon(labels3[b]) == canon(labels[b])).all()
+    pipe.close()
