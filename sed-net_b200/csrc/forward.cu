@@ -91,13 +91,13 @@ static int encoder(const float* const* P, const float* points, const int* idx1, 
     // ---- encoder: three EdgeConv blocks (src/SEDNet.py:80-92)
     // (the first layer's graph depends on the input only: a caller running several networks on the same clouds
     // computes it once with sed_knn_pn and passes it in)
-    if (!idx1) SED_TRY(knn_pn(points, 6LL * N, B, N, k, normal_metric_W, w.idx, 0, st));
+    if (!idx1) SED_TRY(knn_pn(points, 6LL * N, B, N, k, normal_metric_W, w.idx, 0, st, 0));
     SED_TRY(edgeconv(points, 6LL * N, idx1 ? idx1 : w.idx, P[SED_P_ENC_CONV1_W], P[SED_P_ENC_BN1_W], P[SED_P_ENC_BN1_B], B, 6, 64, N,
                      k, 2, kGnEps, 0.2f, w.feats, fb, w.e, st));
-    SED_TRY(knn_l2(w.feats, fb, B, 64, N, k, w.idx, 0, st));
+    SED_TRY(knn_l2(w.feats, fb, B, 64, N, k, w.idx, 0, st, 0));
     SED_TRY(edgeconv(w.feats, fb, w.idx, P[SED_P_ENC_CONV2_W], P[SED_P_ENC_BN2_W], P[SED_P_ENC_BN2_B], B, 64, 64, N, k,
                      2, kGnEps, 0.2f, w.feats + 64LL * N, fb, w.e, st));
-    SED_TRY(knn_l2(w.feats + 64LL * N, fb, B, 64, N, k, w.idx, 0, st));
+    SED_TRY(knn_l2(w.feats + 64LL * N, fb, B, 64, N, k, w.idx, 0, st, 0));
     SED_TRY(edgeconv(w.feats + 64LL * N, fb, w.idx, P[SED_P_ENC_CONV3_W], P[SED_P_ENC_BN3_W], P[SED_P_ENC_BN3_B], B, 64,
                      128, N, k, 2, kGnEps, 0.2f, w.feats + 128LL * N, fb, w.e, st));
 

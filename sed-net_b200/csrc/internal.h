@@ -6,8 +6,11 @@
 namespace sed {
 
 // ---- knn.cu
-int knn_l2(const float* x, long long bstride, int B, int C, int N, int k, void* idx, int idx64, cudaStream_t st);
-int knn_pn(const float* x6, long long bstride, int B, int N, int k, float W, void* idx, int idx64, cudaStream_t st);
+// sorted = 0: the k neighbours of a row may come in any order (enough for EdgeConv, which reduces over them)
+int knn_l2(const float* x, long long bstride, int B, int C, int N, int k, void* idx, int idx64, cudaStream_t st,
+           int sorted = 1);
+int knn_pn(const float* x6, long long bstride, int B, int N, int k, float W, void* idx, int idx64, cudaStream_t st,
+           int sorted = 1);
 int nearest_cos(const float* Q, const float* Cand, int B, int Nq, int Nc, const int* nc_ptr, int d, void* out,
                 int idx64, cudaStream_t st);
 

@@ -409,7 +409,7 @@ namespace sed {
 
 // tensor-core implementations (select_tc.cu); SED_ERR_UNSUPPORTED when the shape is outside their range
 int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn, float W, void* idx, int idx64,
-           cudaStream_t st);
+           cudaStream_t st, int sorted);
 int cos_select_tc(const float* Q, const float* Cand, int B, int Nq, int Nc, const int* nc_ptr, int d, int K,
                   float* kth_out, void* idx_out, int idx64, cudaStream_t st);
 
@@ -423,10 +423,10 @@ static bool use_tc() {
     return v == 1;
 }
 
-int knn_l2(const float* x, long long bstride, int B, int C, int N, int k, void* idx, int idx64, cudaStream_t st) {
+int knn_l2(const float* x, long long bstride, int B, int C, int N, int k, void* idx, int idx64, cudaStream_t st, int sorted) {
     if (!x || !idx || B <= 0 || C <= 0 || C > 128 || N < k || k <= 0) return SED_ERR_ARG;
     if (use_tc()) {
-        const int rc = knn_tc(x, bstride, B, C, N, k, 0, 0.f, idx, idx64, st);
+        const int rc = knn_tc(x, bstride, B, C, N, k, 0, 0.f, idx, idx64, st, sorted);
         if (rc != SED_ERR_UNSUPPORTED) return rc;
     }
     KnnParams p{};
@@ -435,10 +435,10 @@ int knn_l2(const float* x, long long bstride, int B, int C, int N, int k, void* 
     return dispatch_knn_idx<M_L2, L_CHANNEL_MAJOR>(p, B, st);
 }
 
-int knn_pn(const float* x6, long long bstride, int B, int N, int k, float W, void* idx, int idx64, cudaStream_t st) {
+int knn_pn(const float* x6, long long bstride, int B, int N, int k, float W, void* idx, int idx64, cudaStream_t st, int sorted) {
     if (!x6 || !idx || B <= 0 || N < k || k <= 0) return SED_ERR_ARG;
     if (use_tc()) {
-        const int rc = knn_tc(x6, bstride, B, 6, N, k, 1, W, idx, idx64, st);
+        const int rc = knn_tc(x6, bstride, B, 6, N, k, 1, W, idx, idx64, st, sorted);
         if (rc != SED_ERR_UNSUPPORTED) return rc;
     }
     KnnParams p{};

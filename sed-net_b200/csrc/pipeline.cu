@@ -208,7 +208,7 @@ int sed_pipeline_run_forward(sed_pipeline_t* p, const float* points_dev, const f
     SED_CHECK_LAUNCH();
     // first EdgeConv layer's graph: a function of the input only (src/SEDNet.py:80, src/PointNet.py:90-137), shared by
     // the two networks
-    SED_TRY(sed_knn_pn(p->inp, B, N, p->k, 1.0f, p->idx1, 0, st));
+    SED_TRY(knn_pn(p->inp, 6LL * N, B, N, p->k, 1.0f, p->idx1, 0, st, 0));   // neighbour order is irrelevant to EdgeConv
     SED_CUDA(cudaEventRecord(p->ev[1], st));
     // type network (side stream) and instance network (generate_predictions_aug.py:224-229); only the outputs the
     // driver keeps

@@ -39,6 +39,7 @@ struct SelParams {
     float W;
     void* out_idx; int idx64;             // OUT_IDX: (B,Nq,k); OUT_TOP1: (B,Nq)
     float* out_kth;                       // OUT_KTH: (B,Nq)
+    int unsorted;                         // streaming kNN: the k neighbours may be written in any order (EdgeConv's max / sum)
 };
 
 __host__ __device__ __forceinline__ float scale_from_maxabs(float m) {
@@ -785,6 +786,19 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
             if (qq >= p.Nq) break;
             const int rcnt = (int)lds_u32(q_addr + (uint32_t)rr * 4u);
             const uint32_t rk = list_addr + (uint32_t)rr * SS_KEY_ROW, ri = list_addr + SS_KEY_BYTES + (uint32_t)rr * SS_IDX_ROW;
+            if (p.unsorted) {   // consumers that reduce over the neighbours do not need the order: skip the sort
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pos = lane + 32 * h;
+                    if (pos < k) {
+                        const int idx = pos < rcnt ? (int)lds_u16(ri + (uint32_t)pos * 2u) : 0;
+                        const long long o = ((long long)b * p.Nq + qq) * k + pos;
+                        if (p.idx64) reinterpret_cast<long long*>(p.out_idx)[o] = idx;
+                        else reinterpret_cast<int*>(p.out_idx)[o] = idx;
+                    }
+                }
+                continue;
+            }
             unsigned long long e[2];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -1128,7 +1142,7 @@ static int launch_select(const CUtensorMap& qh, const CUtensorMap& ql, const CUt
 
 // kNN over channel-major features: metric L2 (pn = 0) or point x normal (pn = 1).  k <= 64, C <= 64, N < 65536.
 int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn, float W, void* idx, int idx64,
-           cudaStream_t st) {
+           cudaStream_t st, int sorted) {
     if (k > ST_KMAX || C > 64 || N >= 65536 || N < k || (pn && C != 6)) return SED_ERR_UNSUPPORTED;
     const int npad = (N + 127) / 128 * 128;
     const size_t rows = (size_t)B * N;
@@ -1149,7 +1163,7 @@ int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn
         CUtensorMap mh, ml;
         rc = make_map_f16(&mh, hi, B, N, 64);
         if (rc == SED_OK) rc = make_map_f16(&ml, lo, B, N, 64);
-        SelParams p{xx, xx, mx, mx, 1.0f, N, N, npad, k, nullptr, W, idx, idx64, nullptr};
+        SelParams p{xx, xx, mx, mx, 1.0f, N, N, npad, k, nullptr, W, idx, idx64, nullptr, sorted ? 0 : 1};
         // SEDNET_B200_KNN=radix selects the multi-pass radix kernel (A/B comparisons); default: single-pass streaming
         static const bool radix = [] { const char* e = getenv("SEDNET_B200_KNN"); return e && !strcmp(e, "radix"); }();
         if (rc == SED_OK && (radix || (pn && !(W >= 0.f)))) {
@@ -1193,7 +1207,7 @@ int cos_select_tc(const float* Q, const float* Cand, int B, int Nq, int Nc, cons
     if (rc == SED_OK) rc = make_map_f16(&mql, ql, B, Nq, 128);
     if (rc == SED_OK) rc = make_map_f16(&mch, ch, B, Nc, 128);
     if (rc == SED_OK) rc = make_map_f16(&mcl, cl, B, Nc, 128);
-    SelParams p{nullptr, nullptr, nullptr, nullptr, scale, Nq, Nc, 0, K, nc_ptr, 0.f, idx_out, idx64, kth_out};
+    SelParams p{nullptr, nullptr, nullptr, nullptr, scale, Nq, Nc, 0, K, nc_ptr, 0.f, idx_out, idx64, kth_out, 0};
     static const bool radix = [] { const char* e = getenv("SEDNET_B200_KNN"); return e && !strcmp(e, "radix"); }();
     if (rc == SED_OK && kth_out && K <= KS_KMAX && !radix) {
         CUtensorMap xh64, xl64;   // 64-row candidate tiles

@@ -238,3 +238,36 @@ def test_tta_batched_matches_sequential_oracle(dev):
         # sums of up to 12 log-probabilities; a near-tie neighbour swap perturbs isolated points (see config3 test)
         assert float(err.median()) < 1e-5 and float((err.max(1)[0] > 1e-3).float().mean()) < 0.02, (name, float(err.max()))
         assert float((got.argmax(1).cpu() == ref.argmax(1)).float().mean()) > 0.995, name
+
+
+def test_c_abi_error_codes(dev):
+    """Error convention of the C ABI: every entry returns an int, 0 ok, SED_ERR_ARG (-1) for bad arguments,
+    SED_ERR_UNSUPPORTED (-2) outside the compiled range; nothing throws or exits; the Python mirror raises RuntimeError."""
+    from sednet_b200.src import PointNet, _lib
+    lib = _lib.load()
+    x = torch.zeros((1, 3, 64), device=dev)
+    idx = torch.empty((1, 64, 4), dtype=torch.int64, device=dev)
+    nul = C.c_void_p(0)
+    st = _lib.stream()
+    assert lib.sed_knn_l2(nul, 1, 3, 64, 4, _lib.ptr(idx), 1, st) == -1                   # null input
+    assert lib.sed_knn_l2(_lib.ptr(x), 1, 3, 64, 65, _lib.ptr(idx), 1, st) == -1          # k > N
+    assert lib.sed_knn_l2(_lib.ptr(x), 1, 3, 64, 0, _lib.ptr(idx), 1, st) == -1           # k = 0
+    assert lib.sed_knn_l2(_lib.ptr(x), 0, 3, 64, 4, _lib.ptr(idx), 1, st) == -1           # empty batch
+    assert lib.sed_three_nn(_lib.ptr(x), nul, 1, 64, 64, nul, nul, st) == -1
+    assert lib.sed_fit_segments_v2(nul, nul, nul, nul, nul, 1, 64, 1, 20, 0.5, nul, nul, st) == -1
+    assert lib.sed_ms_shift(nul, nul, 1, 64, 128, 5, 0, 3, nul, nul, st) == -1
+    assert lib.sed_pipeline_run_forward(nul, nul, nul, 1, st) == -1
+    h = C.c_void_p()
+    assert lib.sed_pipeline_create(0, 100, 8, 8, C.byref(h)) == -1 and lib.sed_pipeline_create(1, 100, 200, 8, C.byref(h)) == -1
+    assert lib.sed_error_string(-1).decode() == "invalid argument" and lib.sed_error_string(-2).decode().startswith("shape")
+    assert lib.sed_error_string(0).decode() == "ok"
+    with pytest.raises(RuntimeError):
+        PointNet.knn(torch.zeros((1, 3, 8), device=dev), 9, 9)                             # k > N through the mirror
+    with pytest.raises(RuntimeError):
+        PointNet.knn(torch.zeros((1, 3, 8)), 4, 4)                                         # CPU tensor: no fallback
+    # large k / wide features take the CUDA-core fallback and stay exact
+    xw = torch.randn((1, 100, 700), device=dev)
+    got = PointNet.knn(xw, 80, 80).cpu().numpy()
+    ref = O.knn_l2(xw.cpu(), 80).numpy()
+    rows, shared = knn_set_agreement(got, ref)
+    assert rows >= 0.99 and shared >= 0.9999
