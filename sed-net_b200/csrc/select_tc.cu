@@ -40,7 +40,13 @@ struct SelParams {
     void* out_idx; int idx64;             // OUT_IDX: (B,Nq,k); OUT_TOP1: (B,Nq)
     float* out_kth;                       // OUT_KTH: (B,Nq)
     int unsorted;                         // streaming kNN: the k neighbours may be written in any order (EdgeConv's max / sum)
+    int win, soft;                        // streaming kernels: prune window / soft mark (tuning; defaults SS_WIN / KS_WIN, SS_SOFT)
 };
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
 
 __host__ __device__ __forceinline__ float scale_from_maxabs(float m) {
     // power of two s with s * m in [1024, 2048); 1 for empty / degenerate input
@@ -422,8 +428,8 @@ select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_consta
 constexpr int SS_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 select (thread per row)
 constexpr int SS_NC = 64;         // candidates per tile
 constexpr int SS_CAP = 188;       // entries per row buffer (row-major; 752-B / 376-B row strides keep LDS.128 / LDS.64 conflict-free)
-constexpr int SS_WIN = 24;        // a prune leaves between k and k + SS_WIN entries
-constexpr int SS_SOFT = 124;      // soft mark: book a CTA-wide prune
+constexpr int SS_WIN = 12;        // a prune leaves between k and k + SS_WIN entries (swept on the GPU: tools/sweep_prune*.py)
+constexpr int SS_SOFT = 140;      // soft mark: book a CTA-wide prune
 constexpr int SS_LAG = 3;         // ... this many tiles ahead
 constexpr int SS_STAGES = 3;
 constexpr int SS_NBUF = 4;        // TMEM buffers of 128 columns (two 64-column accumulators)
@@ -694,7 +700,7 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
             asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(key_addr + (uint32_t)i * 4u), "r"(SS_NEG_INF));
 
         auto maybe_prune = [&]() {
-            if (__any_sync(0xffffffffu, cnt > SS_CAP - 32)) ss_prune<true>(key_addr, idx_addr, SS_CAP, k, SS_WIN, cnt, thr);
+            if (__any_sync(0xffffffffu, cnt > SS_CAP - 32)) ss_prune<true>(key_addr, idx_addr, SS_CAP, k, p.win, cnt, thr);
         };
         // one 32-candidate chunk of this thread's row: v0 / v1 = the two accumulators
         auto process = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int cbase, uint32_t xc_slot) {
@@ -747,8 +753,8 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
             // warps can drift apart); every warp prunes when it reaches the booked tile.  The private prune of
             // maybe_prune() stays as the overflow guard.
             if (lds_u32(sched_addr + (uint32_t)(j & 15) * 4u) == (uint32_t)j) {
-                ss_prune<true>(key_addr, idx_addr, SS_CAP, k, SS_WIN, cnt, thr);
-            } else if (__any_sync(0xffffffffu, cnt > SS_SOFT)) {
+                ss_prune<true>(key_addr, idx_addr, SS_CAP, k, p.win, cnt, thr);
+            } else if (__any_sync(0xffffffffu, cnt > p.soft)) {
                 bool booked = false;
 #pragma unroll
                 for (int d = 1; d <= SS_LAG; ++d) booked |= lds_u32(sched_addr + (uint32_t)((j + d) & 15) * 4u) == (uint32_t)(j + d);
@@ -990,7 +996,7 @@ kth_stream_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
             asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(key_addr + (uint32_t)i * 4u), "r"(SS_NEG_INF));
 
         auto maybe_prune = [&]() {
-            if (__any_sync(0xffffffffu, cnt > KS_CAP - 32)) ss_prune<false>(key_addr, 0u, KS_CAP, k, KS_WIN, cnt, thr);
+            if (__any_sync(0xffffffffu, cnt > KS_CAP - 32)) ss_prune<false>(key_addr, 0u, KS_CAP, k, p.win, cnt, thr);
         };
         // src/mean_shift.py:130: dist = 2 - 2 x.y ; score = -dist.  nv: valid candidates of the chunk (tail masking)
         auto process = [&](const uint32_t (&v0)[32], const uint32_t (&v1)[32], int nv) {
@@ -1163,7 +1169,9 @@ int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn
         CUtensorMap mh, ml;
         rc = make_map_f16(&mh, hi, B, N, 64);
         if (rc == SED_OK) rc = make_map_f16(&ml, lo, B, N, 64);
-        SelParams p{xx, xx, mx, mx, 1.0f, N, N, npad, k, nullptr, W, idx, idx64, nullptr, sorted ? 0 : 1};
+        static const int ss_win = env_int("SEDNET_B200_SS_WIN", SS_WIN), ss_soft = env_int("SEDNET_B200_SS_SOFT", SS_SOFT);
+        SelParams p{xx, xx, mx, mx, 1.0f, N, N, npad, k, nullptr, W, idx, idx64, nullptr, sorted ? 0 : 1,
+                    min(max(ss_win, 0), SS_CAP - 32 - k), min(max(ss_soft, k + 8), SS_CAP - 33)};
         // SEDNET_B200_KNN=radix selects the multi-pass radix kernel (A/B comparisons); default: single-pass streaming
         static const bool radix = [] { const char* e = getenv("SEDNET_B200_KNN"); return e && !strcmp(e, "radix"); }();
         if (rc == SED_OK && (radix || (pn && !(W >= 0.f)))) {
@@ -1207,7 +1215,9 @@ int cos_select_tc(const float* Q, const float* Cand, int B, int Nq, int Nc, cons
     if (rc == SED_OK) rc = make_map_f16(&mql, ql, B, Nq, 128);
     if (rc == SED_OK) rc = make_map_f16(&mch, ch, B, Nc, 128);
     if (rc == SED_OK) rc = make_map_f16(&mcl, cl, B, Nc, 128);
-    SelParams p{nullptr, nullptr, nullptr, nullptr, scale, Nq, Nc, 0, K, nc_ptr, 0.f, idx_out, idx64, kth_out, 0};
+    static const int ks_win = env_int("SEDNET_B200_KS_WIN", KS_WIN);
+    SelParams p{nullptr, nullptr, nullptr, nullptr, scale, Nq, Nc, 0, K, nc_ptr, 0.f, idx_out, idx64, kth_out, 0,
+                min(max(ks_win, 0), max(KS_CAP - 32 - K - 8, 0)), 0};
     static const bool radix = [] { const char* e = getenv("SEDNET_B200_KNN"); return e && !strcmp(e, "radix"); }();
     if (rc == SED_OK && kth_out && K <= KS_KMAX && !radix) {
         CUtensorMap xh64, xl64;   // 64-row candidate tiles
