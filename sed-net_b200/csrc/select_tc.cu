@@ -427,12 +427,12 @@ select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_consta
 // squared norm of +inf, so their score is -inf (or NaN) and never passes the threshold test.
 constexpr int SS_THREADS = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 select (thread per row)
 constexpr int SS_NC = 64;         // candidates per tile
-constexpr int SS_CAP = 188;       // entries per row buffer (row-major; 752-B / 376-B row strides keep LDS.128 / LDS.64 conflict-free)
+constexpr int SS_CAP = 228;       // entries per row buffer (row-major; 912-B / 456-B row strides keep LDS.128 / LDS.64 conflict-free)
 constexpr int SS_WIN = 12;        // a prune leaves between k and k + SS_WIN entries (swept on the GPU: tools/sweep_prune*.py)
-constexpr int SS_SOFT = 140;      // soft mark: book a CTA-wide prune
+constexpr int SS_SOFT = 164;      // soft mark: book a CTA-wide prune
 constexpr int SS_LAG = 3;         // ... this many tiles ahead
 constexpr int SS_STAGES = 3;
-constexpr int SS_NBUF = 4;        // TMEM buffers of 128 columns (two 64-column accumulators)
+constexpr int SS_NBUF = 3;        // TMEM buffers of 128 columns (two 64-column accumulators); columns [384,448): the query tile
 constexpr int SS_XCRING = 8;      // candidate-norm slices in flight: >= SS_STAGES + SS_NBUF (producer's maximum lead)
 constexpr uint32_t SS_XPART = 64 * 128;                  // one candidate tile part: 64 rows x 64 channels fp16
 constexpr uint32_t SS_KEY_ROW = SS_CAP * 4, SS_IDX_ROW = SS_CAP * 2;
@@ -576,22 +576,24 @@ __device__ __noinline__ void ss_prune(uint32_t key_row, uint32_t idx_row, int ca
     thr_io = thr;
 }
 
+// The query tile (FP16 hi and lo, 64 channels) lives in TMEM for the whole CTA (A operand from TMEM, as in the K-th
+// kernel below): the 32 KB of shared memory it would take go to the row buffers instead.
 template <int MODE>
 __global__ void __launch_bounds__(SS_THREADS, 1)
-select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
-                     const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, SelParams p) {
-    constexpr uint32_t QPART = BOX_BYTES;                          // 128 rows x 64 channels fp16
+select_stream_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl,
+                     const __half* __restrict__ qh, const __half* __restrict__ ql, SelParams p) {
     constexpr uint32_t XSTAGE = 2 * SS_XPART;                      // hi + lo
     constexpr uint32_t BUF_COLS = 128;
+    constexpr uint32_t Q_COL = SS_NBUF * BUF_COLS;                 // 384: hi in [384,416), lo in [416,448)
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw0 = smem_u32(smem_raw);
     const uint32_t smem_base = (raw0 + 1023u) & ~1023u;
-    const uint32_t q_addr = smem_base;
-    const uint32_t x_addr = q_addr + 2 * QPART;
+    const uint32_t x_addr = smem_base;
     const uint32_t list_addr = x_addr + SS_STAGES * XSTAGE;
     const uint32_t xc_addr = list_addr + SS_KEY_BYTES + SS_IDX_BYTES;       // [SS_XCRING][64] candidate squared norms
-    const uint32_t bar_base = xc_addr + SS_XCRING * SS_NC * 4;
+    const uint32_t rc_addr = xc_addr + SS_XCRING * SS_NC * 4;               // [128] final per-row counts
+    const uint32_t bar_base = rc_addr + ST_M * 4;
     const uint32_t bar_q_full = bar_base;
     const uint32_t bar_x_full = bar_base + 8;
     const uint32_t bar_x_empty = bar_x_full + 8 * SS_STAGES;
@@ -608,7 +610,7 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
     if (threadIdx.x < 16) sts_u32(sched_addr + threadIdx.x * 4, 0xffffffffu);
 
     if (threadIdx.x == 0) {
-        mbar_init(bar_q_full, 1);
+        mbar_init(bar_q_full, 128);
         for (int s = 0; s < SS_STAGES; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
         for (int i = 0; i < SS_NBUF; ++i) { mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_s_empty + 8 * i, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -625,9 +627,6 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
     if (warp == 0) {
         // ============================================================ TMA producer
         if (elect_one()) {
-            mbar_expect_tx(bar_q_full, 2 * QPART);
-            tma_load_3d(q_addr, &map_qh, bar_q_full, 0, q0, b);
-            tma_load_3d(q_addr + QPART, &map_ql, bar_q_full, 0, q0, b);
             for (int j = 0; j < T; ++j) {
                 const int s = j % SS_STAGES;
                 if (j >= SS_STAGES) mbar_wait_relaxed<256>(bar_x_empty + 8 * s, ((j / SS_STAGES) - 1) & 1);
@@ -656,24 +655,23 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
                 if (MODE == SEL_PN) {
 #pragma unroll
                     for (int a = 0; a < 2; ++a) {
-                        // channels [0,16): points (3 used), [16,32): normals (3 used): one K-step each
+                        // channels [0,16): points (3 used), [16,32): normals (3 used): one K-step (8 TMEM columns) each
 #pragma unroll
                         for (int term = 0; term < 3; ++term) {
-                            const uint32_t qa = q_addr + ((term == 2) ? QPART : 0);         // Qh, Qh, Ql
+                            const uint32_t qa = tmem + Q_COL + ((term == 2) ? 32u : 0u);    // Qh, Qh, Ql   (TMEM)
                             const uint32_t xb = xs + ((term == 1) ? SS_XPART : 0);          // Xh, Xl, Xh
-                            umma_ss(d + a * 64, make_desc(qa + a * 32, 16), make_desc(xb + a * 32, 16), IDESC, term > 0);
+                            umma_ts(d + a * 64, qa + a * 8, make_desc(xb + a * 32, 16), IDESC, term > 0);
                         }
                     }
                 } else {
 #pragma unroll
                     for (int term = 0; term < 3; ++term) {
-                        const uint32_t qa = q_addr + ((term == 2) ? QPART : 0);
+                        const uint32_t qa = tmem + Q_COL + ((term == 2) ? 32u : 0u);
                         const uint32_t xb = xs + ((term == 1) ? SS_XPART : 0);
                         const uint32_t dd = d + (term == 0 ? 0u : 64u);                     // hi.hi | cross terms
 #pragma unroll
                         for (int ks = 0; ks < 4; ++ks)
-                            umma_ss(dd, make_desc(qa + ks * 32, 16), make_desc(xb + ks * 32, 16), IDESC,
-                                    (ks > 0 || term == 2) ? 1u : 0u);
+                            umma_ts(dd, qa + ks * 8, make_desc(xb + ks * 32, 16), IDESC, (ks > 0 || term == 2) ? 1u : 0u);
                     }
                 }
                 tc_commit(bar_s_full + 8 * buf);
@@ -686,6 +684,27 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
         const int row = quarter * 32 + lane;
         const int q = q0 + row;
         const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        {   // this thread's query row -> TMEM columns [384,416) (hi) and [416,448) (lo)
+            const long long ro = ((long long)b * p.Nq + min(q, p.Nq - 1)) * 64;
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const uint4* g4 = reinterpret_cast<const uint4*>((part ? ql : qh) + ro);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t w[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (q < p.Nq) v = __ldg(g4 + c * 4 + i);
+                        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+                    }
+                    tmem_st16(tmem + lane_addr + Q_COL + part * 32u + c * 16u, w);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_q_full);
+        }
         const float sq = scale_from_maxabs(p.maxabs_q[b]);
         const float sc = scale_from_maxabs(p.maxabs_c[b]);
         const float inv2 = 2.0f * ((1.0f / sq) * (1.0f / sc));          // power of two: products below are exact
@@ -780,7 +799,7 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
         // ---- exact top-k of the survivors; the per-row counts go to shared memory (the Q tile is dead: every MMA
         // completed before the last s_full) for the sort below
         ss_prune<true>(key_addr, idx_addr, SS_CAP, k, 0, cnt, thr);
-        sts_u32(q_addr + (uint32_t)row * 4u, (uint32_t)cnt);
+        sts_u32(rc_addr + (uint32_t)row * 4u, (uint32_t)cnt);
     }
     // ================================================================ sort: one warp per row, all six warps
     __syncwarp();
@@ -790,7 +809,7 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
         for (int rr = warp; rr < ST_M; rr += SS_THREADS / 32) {
             const int qq = q0 + rr;
             if (qq >= p.Nq) break;
-            const int rcnt = (int)lds_u32(q_addr + (uint32_t)rr * 4u);
+            const int rcnt = (int)lds_u32(rc_addr + (uint32_t)rr * 4u);
             const uint32_t rk = list_addr + (uint32_t)rr * SS_KEY_ROW, ri = list_addr + SS_KEY_BYTES + (uint32_t)rr * SS_IDX_ROW;
             if (p.unsorted) {   // consumers that reduce over the neighbours do not need the order: skip the sort
 #pragma unroll
@@ -853,15 +872,15 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_co
 }
 
 template <int MODE>
-static int launch_stream(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& xh, const CUtensorMap& xl,
+static int launch_stream(const CUtensorMap& xh, const CUtensorMap& xl, const __half* qh, const __half* ql,
                          const SelParams& p, int B, cudaStream_t st) {
-    constexpr size_t smem = (size_t)2 * BOX_BYTES + (size_t)SS_STAGES * 2 * SS_XPART + SS_KEY_BYTES + SS_IDX_BYTES +
-                            SS_XCRING * SS_NC * 4 + 1024 + 256;
+    constexpr size_t smem = (size_t)SS_STAGES * 2 * SS_XPART + SS_KEY_BYTES + SS_IDX_BYTES + SS_XCRING * SS_NC * 4 +
+                            ST_M * 4 + 1024 + 256;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     auto kern = select_stream_kernel<MODE>;
     SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((p.Nq + ST_M - 1) / ST_M, B);
-    kern<<<grid, SS_THREADS, smem, st>>>(qh, ql, xh, xl, p);
+    kern<<<grid, SS_THREADS, smem, st>>>(xh, xl, qh, ql, p);
     SED_CHECK_LAUNCH();
     return SED_OK;
 }
@@ -1182,7 +1201,7 @@ int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn
             rc = make_map_f16(&xh, hi, B, N, 64, SS_NC);
             if (rc == SED_OK) rc = make_map_f16(&xl, lo, B, N, 64, SS_NC);
             if (rc == SED_OK)
-                rc = pn ? launch_stream<SEL_PN>(mh, ml, xh, xl, p, B, st) : launch_stream<SEL_L2>(mh, ml, xh, xl, p, B, st);
+                rc = pn ? launch_stream<SEL_PN>(xh, xl, hi, lo, p, B, st) : launch_stream<SEL_L2>(xh, xl, hi, lo, p, B, st);
         }
     }
     cudaFreeAsync(buf, st);
