@@ -157,7 +157,8 @@ int sed_ms_bandwidth(const float* X, int B, int N, int d, int K, float min_bw, f
 
 /* src/mean_shift.py:45-79 mean_shift_: `iterations` fixed shifts on the unit hypersphere.
  *   X (B,N,d), bw (B) device, kernel_type 0 gaussian / 1 epanechnikov, prec_mode 0 = FP32 FFMA (reference
- *   operation order), tcgen05 modes (d == 128) with FP16 hi/lo split operands and FP32 accumulation:
+ *   operation order), tcgen05 modes (d <= 128, zero-padded to 128 columns) with FP16 hi/lo split operands and FP32
+ *   accumulation:
  *   1 = S from 3 MMAs (Qh.Xh + Qh.Xl + Ql.Xh), O from 2 (Ph.Xh + Ph.Xl);  3 = S from 3, O from 1 (Ph.Xh);
  *   2 = single FP16 pass for both (fast, not FP32-faithful).
  *   out (B,N,d); tmp (B,N,d) scratch (ping-pong). */

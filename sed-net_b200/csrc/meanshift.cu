@@ -385,7 +385,11 @@ int sed_ms_shift(const float* X, const float* bw, int B, int N, int d, int itera
         SED_CUDA(cudaMemcpyAsync(out, X, (size_t)B * N * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
         return SED_OK;
     }
-    if (prec_mode >= 1 && prec_mode <= 3) return ms_shift_tc(X, bw, B, N, d, iterations, kernel_type, prec_mode, out, tmp, st);
+    if (prec_mode >= 1 && prec_mode <= 3) {
+        const int rc = ms_shift_tc(X, bw, B, N, d, iterations, kernel_type, prec_mode, out, tmp, st);
+        if (rc != SED_ERR_UNSUPPORTED) return rc;
+        prec_mode = 0;   // shape outside the tensor-core kernel's range: the FP32 FFMA kernel
+    }
     if (prec_mode != 0) return SED_ERR_ARG;
     // XT lives in the second half of tmp's allocation?  No: tmp is exactly (B,N,d); the channel-major copy of X is
     // allocated from the stream-ordered pool (freed after the last iteration is enqueued).

@@ -357,11 +357,15 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
     }
 }
 
-// x (rows, 128) f32 -> hi = fp16(8x), lo = fp16(8x - hi)
-__global__ void split_f16_kernel(const float* __restrict__ x, long long n, __half* __restrict__ hi, __half* __restrict__ lo) {
+// x (rows, d) f32, d <= 128 a multiple of 4 -> (rows, 128) hi = fp16(8x), lo = fp16(8x - hi), columns >= d zero (zero
+// columns change neither the dot products nor the norms: narrower embeddings run on the same kernel)
+__global__ void split_f16_kernel(const float* __restrict__ x, long long n, int d, __half* __restrict__ hi, __half* __restrict__ lo) {
     const long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;
-    const float4 v = *reinterpret_cast<const float4*>(x + i);
+    const long long row = i / TC_D;
+    const int col = (int)(i - row * TC_D);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < d) v = *reinterpret_cast<const float4*>(x + row * d + col);
     const float a[4] = {v.x * kOperandScale, v.y * kOperandScale, v.z * kOperandScale, v.w * kOperandScale};
     __half h[4], l[4];
 #pragma unroll
@@ -394,7 +398,8 @@ static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const TcParam
 int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type, int prec_mode,
                 float* out, float* tmp, cudaStream_t st) {
     (void)tmp;
-    if (d != TC_D) return SED_ERR_UNSUPPORTED;
+    if (d > TC_D || d <= 0 || (d & 3)) return SED_ERR_UNSUPPORTED;
+    const bool padded = d < TC_D;      // the kernel works on 128-wide rows: pad with zero columns, strip them at the end
     const bool has_lo = (prec_mode == 1 || prec_mode == 3);
     const size_t elems = (size_t)B * N * TC_D;
     // one CTA per SM: whole waves of query tiles, then the partial wave split by key range over the idle SMs
@@ -409,13 +414,15 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
     // fp16 operands: X (hi, lo) and two ping-pong Q buffers (hi, lo)
     ensure_pool_config();
     __half* buf = nullptr;
-    SED_CUDA(cudaMallocAsync((void**)&buf, elems * sizeof(__half) * 6 + part_bytes + (size_t)(rem + 1) * sizeof(int), st));
-    float* part_o = reinterpret_cast<float*>(buf + 6 * elems);
+    const size_t pad_bytes = padded ? elems * sizeof(float) : 0;
+    SED_CUDA(cudaMallocAsync((void**)&buf, elems * sizeof(__half) * 6 + pad_bytes + part_bytes + (size_t)(rem + 1) * sizeof(int), st));
+    float* out128 = padded ? reinterpret_cast<float*>(buf + 6 * elems) : out;
+    float* part_o = reinterpret_cast<float*>(reinterpret_cast<char*>(buf + 6 * elems) + pad_bytes);
     int* part_cnt = reinterpret_cast<int*>(reinterpret_cast<char*>(part_o) + part_bytes);
     if (cudaMemsetAsync(part_cnt, 0, (size_t)(rem + 1) * sizeof(int), st) != cudaSuccess) { cudaFreeAsync(buf, st); return SED_ERR_CUDA_BASE - 1; }
     __half *xh = buf, *xl = buf + elems, *qh[2] = {buf + 2 * elems, buf + 4 * elems},
            *ql[2] = {buf + 3 * elems, buf + 5 * elems};
-    split_f16_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, st>>>(X, (long long)elems, xh, xl);
+    split_f16_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, st>>>(X, (long long)elems, d, xh, xl);
     ++g_sed_launches;
     CUtensorMap mxh, mxl;
     int rc = make_map_f16(&mxh, xh, B, N, TC_D);
@@ -424,12 +431,16 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
         // iteration 0 reads Q = X; iteration it > 0 reads ping-pong buffer (it-1)&1 and writes buffer it&1
         const __half* cqh = it == 0 ? xh : qh[(it - 1) & 1];
         const __half* cql = it == 0 ? xl : ql[(it - 1) & 1];
-        TcParams p{cqh, cql, bw, it == iterations - 1 ? out : nullptr, qh[it & 1], has_lo ? ql[it & 1] : nullptr, N,
+        TcParams p{cqh, cql, bw, it == iterations - 1 ? out128 : nullptr, qh[it & 1], has_lo ? ql[it & 1] : nullptr, N,
                    kernel_type, qtc, full, parts, tpp, part_o, part_cnt, full + rem * parts};
         rc = prec_mode == 1   ? launch_tc<3, 2>(mxh, mxl, p, B, st)
              : prec_mode == 3 ? launch_tc<3, 1>(mxh, mxl, p, B, st)
                               : launch_tc<1, 1>(mxh, mxl, p, B, st);
     }
+    if (rc == SED_OK && padded &&
+        cudaMemcpy2DAsync(out, (size_t)d * sizeof(float), out128, (size_t)TC_D * sizeof(float), (size_t)d * sizeof(float),
+                          (size_t)B * N, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        rc = SED_ERR_CUDA_BASE - 1;
     cudaFreeAsync(buf, st);
     return rc;
 }

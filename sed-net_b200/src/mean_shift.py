@@ -12,9 +12,16 @@ MAX_CENTERS = 512
 class MeanShift:
     def __init__(self, prec_mode=None):
         """prec_mode of sed_ms_shift (include/sednet_b200.h): 0 FP32 FFMA, 1 / 3 tcgen05 FP16 hi/lo split (3+2 / 3+1 MMAs),
-        2 plain FP16; None = $SEDNET_B200_MS_PREC or 0."""
+        2 plain FP16; None = $SEDNET_B200_MS_PREC if set, otherwise automatic: the FP32-faithful tensor-core mode 3
+        (embeddings up to 128 wide, zero-padded; identical labels, <= 4e-6 from mode 0), else the FFMA kernel."""
         import os
-        self.prec_mode = int(os.environ.get("SEDNET_B200_MS_PREC", "0")) if prec_mode is None else prec_mode
+        env = os.environ.get("SEDNET_B200_MS_PREC")
+        self.prec_mode = prec_mode if prec_mode is not None else (int(env) if env is not None else None)
+
+    def _mode(self, d):
+        if self.prec_mode is not None:
+            return self.prec_mode
+        return 3 if d <= 128 and d % 4 == 0 else 0
 
     # -- src/mean_shift.py:19-43
     def mean_shift(self, X, num_samples, quantile, iterations, kernel_type="gaussian", bw=None, nms=True):
@@ -38,7 +45,7 @@ class MeanShift:
         bw = torch.as_tensor(b, dtype=torch.float32, device=X.device).reshape(1).contiguous()
         out, tmp = torch.empty_like(X), torch.empty_like(X)
         kt = 0 if kernel_type == "gaussian" else 1
-        _lib.call("sed_ms_shift", _lib.ptr(X), _lib.ptr(bw), 1, N, d, int(iterations), kt, self.prec_mode,
+        _lib.call("sed_ms_shift", _lib.ptr(X), _lib.ptr(bw), 1, N, d, int(iterations), kt, self._mode(d),
                   _lib.ptr(out), _lib.ptr(tmp), _lib.stream())
         return out, X
 

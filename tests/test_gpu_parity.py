@@ -491,3 +491,20 @@ def test_pipeline_guard_loop_with_planted_embeddings(dev):
     for b in range(B):
         assert (canon(labels3[b]) == canon(labels[b])).all()
     pipe.close()
+
+
+def test_meanshift_default_mode_and_narrow_embedding(dev):
+    """MeanShift() picks the FP32-faithful tensor-core mode; a narrower embedding (d = 64) runs on the same kernel
+    zero-padded to 128 columns: both reproduce the oracle's partition, bandwidth and shifted points."""
+    from sednet_b200.src.mean_shift import MeanShift
+    _, _, lab, _, _ = synth.make_cloud(91, 2500, n_patches=7, min_pts=250)
+    for d in (128, 64):
+        X = t(synth.make_embedding(lab, d, 0.02, 17))
+        ms = MeanShift()
+        assert ms._mode(d) == 3 and MeanShift()._mode(50) == 0
+        newX, center, bw, labels = ms.mean_shift(X.to(dev), 10000, 0.015, 20)
+        with torch.no_grad():
+            rX, rc, rbw, rlab = O.mean_shift(X, 10000, 0.015, 20)
+        assert (canon(labels.cpu().numpy()) == canon(rlab.numpy())).all() and (canon(rlab.numpy()) == canon(lab)).all()
+        assert abs(float(bw) - float(rbw)) < 1e-4 * float(rbw)
+        assert float((newX.cpu() - rX).abs().max()) < 1e-4 and center.shape == rc.shape
