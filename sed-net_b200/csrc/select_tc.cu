@@ -770,7 +770,9 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
             // CTA-wide prunes: the four warps share the TMEM ring, so a warp that prunes alone stalls the others after
             // ~2 tiles.  A warp whose buffers pass the soft mark books a prune SS_LAG tiles ahead (further than the
             // warps can drift apart); every warp prunes when it reaches the booked tile.  The private prune of
-            // maybe_prune() stays as the overflow guard.
+            // maybe_prune() stays as the overflow guard.  The booking words are plain shared-memory hints written and
+            // polled without synchronisation on purpose (compute-sanitizer racecheck reports them): a missed hint only
+            // moves a warp's prune to a later tile, and the result does not depend on when a row is pruned.
             if (lds_u32(sched_addr + (uint32_t)(j & 15) * 4u) == (uint32_t)j) {
                 ss_prune<true>(key_addr, idx_addr, SS_CAP, k, p.win, cnt, thr);
             } else if (__any_sync(0xffffffffu, cnt > p.soft)) {
