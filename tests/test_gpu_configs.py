@@ -271,3 +271,33 @@ def test_c_abi_error_codes(dev):
     ref = O.knn_l2(xw.cpu(), 80).numpy()
     rows, shared = knn_set_agreement(got, ref)
     assert rows >= 0.99 and shared >= 0.9999
+
+
+def test_config1_single_cloud_2048(dev):
+    """configs[0]: one 2048-point cloud -- forward of both networks, guarded mean-shift, plane fit -- through the
+    host-buffer C-ABI step against the oracle's end_to_end, plus the plane fit of the largest planar ground-truth segment."""
+    from sednet_b200.pipeline import Pipeline
+    from sednet_b200.src.primitive_forward import Fit
+    Np, k = 2048, 64
+    pts, nrm, lab, typ = synth.make_batch(1, Np, seed0=2048, n_patches=6)
+    sd_t, sd_i = synth.make_state_dict(0), synth.make_state_dict(1, randomize_gn=True)
+    pipe = Pipeline(1, Np, k)
+    pipe.set_weights(sd_t, sd_i)
+    out = pipe.run_host(t(pts).pin_memory(), t(nrm).pin_memory(), 0.015, 50, 0)
+    with torch.no_grad():
+        ref = O.end_to_end({kk: t(v) for kk, v in sd_t.items()}, {kk: t(v) for kk, v in sd_i.items()}, t(pts), t(nrm), k)[0]
+    assert (canon(out["labels"][0].numpy()) == canon(ref["labels"])).all()
+    assert (out["pred_type"][0].numpy() == ref["types"]).mean() > 0.999
+    assert abs(float(out["bw"][0]) - ref["bw"]) < 5e-3 * ref["bw"]
+    pipe.close()
+    planes = [s for s in range(int(lab[0].max()) + 1) if typ[0][lab[0] == s][0] == 1]
+    if planes:
+        s = max(planes, key=lambda s_: int((lab[0] == s_).sum()))
+        m = lab[0] == s
+        P, W = t(pts[0][m]), torch.ones((int(m.sum()), 1))
+        a, d = Fit().fit_plane_torch(P.to(dev), None, W.to(dev))
+        ra, rd = O.fit_plane(P, None, W)
+        got = np.concatenate([a.cpu().numpy().ravel(), [float(d)]])
+        want = np.concatenate([ra.numpy().ravel(), [float(rd)]])
+        got = got if got[:3] @ want[:3] > 0 else -got
+        assert rel_err(got, want) < 1e-4
