@@ -231,6 +231,34 @@ int sed_inst_edges(const int* idx3, const int64_t* insts, int n, int strict, uin
 int sed_face_face_map(const float* points, const int64_t* insts, const int* idx3, const int64_t* primitive_ids, int n_ids,
                       int n, int nn_num_thresh, uint8_t* mat, sed_stream_t stream);
 
+/* ------------------------------------------------------------------ evaluation (src/segment_utils.py, src/utils.py) */
+
+/* The integer tables from which the driver's matching / IoU metrics are computed (SIOU_matched_segments[_usecd]
+ * src/segment_utils.py:140-243, mean_IOU_primitive_segment[_usecd] :359-495, relaxed_iou_fast :609-627,
+ * compute_type_miou_abc :300-357), one pass over the points.  pred, gt (B,N) int64 labels (values outside [0,K) are
+ * ignored, e.g. the -1 background of :326-331); type_pred, type_gt (B,N) int64 in [0,T) or NULL.  K <= 64, T <= 16.
+ *   confusion (B,K,K) [r][c] = #points with pred r and gt c;   npred, ngt (B,K) segment sizes;
+ *   pred_types, gt_types (B,K,T) histogram of the point types of every segment;
+ *   gt_first (B,K) index of the first point of every gt segment (N when empty: `gt_prim[gt_indices][0]`, :411,478). */
+int sed_segment_tables(const int64_t* pred, const int64_t* gt, const int64_t* type_pred, const int64_t* type_gt, int B, int N,
+                       int K, int T, int* confusion, int* npred, int* ngt, int* pred_types, int* gt_types, int* gt_first,
+                       sed_stream_t stream);
+
+/* primitive_type_segment_torch, src/segment_utils.py:509-517: out (T,K)[l][k] = sum_n [types[n] == l] * weights[n,k]
+ * (types (N) int64, weights (N,K) f32; the caller takes the argmax over l).  T <= 16. */
+int sed_type_vote_weighted(const int64_t* types, const float* weights, int N, int K, int T, float* out, sed_stream_t stream);
+
+/* chamfer_distance, src/utils.py:273-296: a (B,n,3), b (B,m,3) -> min_a (B,n) = min_j |a_i - b_j|^2, min_b (B,m) (FP32,
+ * the reference's operation order); the caller averages ((mean min_a + mean min_b) / 2). */
+int sed_chamfer_min(const float* a, const float* b, int B, int n, int m, float* min_a, float* min_b, sed_stream_t stream);
+
+/* The chamfer terms of ALL matched segment pairs of mean_IOU_primitive_segment_usecd (src/segment_utils.py:473) in one
+ * pass: pred2gt, gt2pred (B,K) int32 matched partner of every segment or -1.  min_pred (B,N)[i] = distance^2 from point
+ * i to the nearest point of the gt segment matched to i's predicted segment; min_gt (B,N)[i] = to the nearest point of
+ * the predicted segment matched to i's gt segment; +inf when unmatched.  K <= 254. */
+int sed_matched_chamfer(const float* points, const int64_t* pred, const int64_t* gt, const int* pred2gt, const int* gt2pred, int B,
+                        int N, int K, float* min_pred, float* min_gt, sed_stream_t stream);
+
 /* LeastSquares.lstsq(A, Y, lamb) src/fitting_utils.py:36-65 for one (m,3) system: x (3); status 0 full rank (QR
  * branch), 2 regularised branch (best_lambda :68-85). */
 int sed_lstsq3(const float* A, const float* Y, int m, float* x, int* status, sed_stream_t stream);

@@ -23,7 +23,8 @@ def get_edges_between_insts(points, insts, strict=True):
     insts = _lib.require_cuda(torch_type(insts), torch.int64, "insts")
     n = points.shape[0]
     out = torch.empty(n, dtype=torch.uint8, device=points.device)
-    _lib.call("sed_inst_edges", _lib.ptr(_idx3(points)), _lib.ptr(insts), n, 1 if strict else 0, _lib.ptr(out), _lib.stream())
+    idx3 = _idx3(points)
+    _lib.call("sed_inst_edges", _lib.ptr(idx3), _lib.ptr(insts), n, 1 if strict else 0, _lib.ptr(out), _lib.stream())
     return out.bool()
 
 
@@ -35,6 +36,7 @@ def face_face_inter_map(points, insts, primitive_ids, nn_num_thresh=3):
                             torch.int64, "primitive_ids")
     n = points.shape[0]
     mat = torch.empty((30, 30), dtype=torch.uint8, device=points.device)
-    _lib.call("sed_face_face_map", _lib.ptr(points), _lib.ptr(insts), _lib.ptr(_idx3(points)), _lib.ptr(ids), int(ids.numel()),
+    idx3 = _idx3(points)
+    _lib.call("sed_face_face_map", _lib.ptr(points), _lib.ptr(insts), _lib.ptr(idx3), _lib.ptr(ids), int(ids.numel()),
               n, int(nn_num_thresh), _lib.ptr(mat), _lib.stream())
     return mat.bool().cpu()

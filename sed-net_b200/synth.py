@@ -149,6 +149,27 @@ def make_touching_instances(seed, n):
     return pts[perm], lab[perm]
 
 
+def make_metric_case(seed, n):
+    """Labels for the evaluation metrics: a cloud of analytic patches with its ground-truth instance /
+    type labels, and a 'prediction' that merges two instances, splits one, mislabels 3 % of the points and gets some
+    per-point types wrong.  Returns points (n,3) f32, gt (n,), type_gt (n,), pred (n,), type_pred (n,) (all int64;
+    pred labels are contiguous 0..C-1)."""
+    pts, _, lab, typ, _ = make_cloud(seed, n, n_patches=9, min_pts=150)
+    rng = np.random.default_rng(seed + 1000)
+    pred = lab.copy()
+    pred[pred == 1] = 0                                        # merge
+    big = int(np.argmax(np.bincount(lab)))
+    idx = np.flatnonzero(lab == big)
+    pred[idx[: len(idx) // 3]] = int(lab.max()) + 1            # split
+    flip = rng.choice(n, n * 3 // 100, replace=False)
+    pred[flip] = rng.integers(0, int(pred.max()) + 1, len(flip))
+    _, pred = np.unique(pred, return_inverse=True)             # contiguous ids
+    type_pred = typ.copy()
+    wrong = rng.choice(n, n // 10, replace=False)
+    type_pred[wrong] = rng.choice([1, 3, 4, 5, 0, 8], len(wrong))
+    return pts, lab.astype(np.int64), typ.astype(np.int64), pred.astype(np.int64), type_pred.astype(np.int64)
+
+
 def make_embedding(labels, dim=128, sigma=0.01, seed=0):
     """Unit-norm embedding with one well separated mode per label:
     normalize(centroid[label] + sigma * randn)."""

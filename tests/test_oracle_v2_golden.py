@@ -104,3 +104,26 @@ def test_stage1_text_files_round_trip(tmp_path):
     back = wire.read_stage1(str(tmp_path), 42)
     assert np.abs(back["points"] - pts).max() <= 5e-5 and np.array_equal(back["inst"], lab) and np.array_equal(back["types"], typ)
     assert back["edges"].shape == (500, 2) and np.abs(back["edges"].sum(1) - 1).max() < 2e-4
+
+
+def test_metrics_oracle_matches_reference():
+    """oracle/oracle_metrics.py against the values recorded from the unmodified src/segment_utils.py / src/utils.py."""
+    import oracle_metrics as OM
+    g = np.load(os.path.join(ROOT, "tests", "golden", "metrics.npz"))
+    *seeds, n = [int(v) for v in g["cfg"]]
+    for case, seed in enumerate(seeds):
+        pts, gt, typ_gt, pred, typ_pred = synth.make_metric_case(seed, n)
+        if case == 3:
+            pts = (pts * 3.0).astype(np.float32)
+        w = OM.one_hot(pred, int(np.unique(pred).shape[0]))
+        for usecd in (0, 1):
+            o = OM.siou_matched_segments(gt.copy(), pred.copy(), typ_pred.copy(), typ_gt.copy(), w, pts if usecd else None)
+            assert np.array_equal(np.array([o[0], o[1], o[4]]), g[f"c{case}_u{usecd}"])
+            assert np.array_equal(np.array(o[3]), g[f"c{case}_u{usecd}_pairs"])
+        logits = np.random.default_rng(seed).normal(size=(1, n, 10)).astype(np.float32)
+        logits[0, np.arange(n), typ_pred] += 3.0
+        I_gt = gt.copy()
+        I_gt[:50] = -1
+        assert abs(float(OM.compute_type_miou_abc(logits[0], typ_gt.copy(), pred.copy(), I_gt)) - float(g[f"c{case}_abc"])) < 1e-7
+        cd = OM.chamfer_distance(pts[pred == 0], pts[gt == 1])
+        assert abs(cd - float(g[f"c{case}_cd"])) < 1e-7 * max(1.0, float(g[f"c{case}_cd"]))
