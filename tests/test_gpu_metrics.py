@@ -82,3 +82,29 @@ def test_metrics_at_full_size_vs_oracle(dev):
     _lib.call("sed_chamfer_min", _lib.ptr(a), _lib.ptr(b), 1, 3000, 4100, _lib.ptr(ma), _lib.ptr(mb), _lib.stream())
     d = torch.sum((a[0].cpu()[:, None, :] - b[0].cpu()[None, :, :]) ** 2, 2)
     assert torch.equal(ma[0].cpu(), d.min(1)[0]) and torch.equal(mb[0].cpu(), d.min(0)[0])
+
+
+def test_driver_flow_end_to_end(dev):
+    """The per-shape body of generate_predictions_aug.py written against the drop-in modules
+    (examples/predict_like_driver.py) against the oracle chain: labels (canonicalised), types and metrics identical."""
+    import importlib.util
+    import oracle as O
+    from util import canon
+    spec = importlib.util.spec_from_file_location("predict_like_driver", os.path.join(ROOT, "examples", "predict_like_driver.py"))
+    drv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(drv)
+    n, k = 2000, 32
+    pts, nrm, lab, typ, _ = synth.make_cloud(555, n, n_patches=6)
+    sd_t, sd_i = synth.make_state_dict(0), synth.make_state_dict(1, randomize_gn=True)
+    out = drv.predict_shape(drv.build_model(sd_t, k), drv.build_model(sd_i, k), t(pts)[None], t(nrm)[None], lab[None], typ[None])
+    with torch.no_grad():
+        ref = O.end_to_end({kk: t(v) for kk, v in sd_t.items()}, {kk: t(v) for kk, v in sd_i.items()}, t(pts)[None], t(nrm)[None], k)[0]
+    assert (canon(out["cluster_ids"]) == canon(ref["labels"])).all()
+    assert (out["pred_primitives"] == ref["types"]).mean() > 0.999
+    rl = canon(ref["labels"])
+    w = OM.one_hot(rl, int(np.unique(rl).shape[0]))
+    o = OM.siou_matched_segments(lab.copy(), rl, ref["types"].copy(), typ.copy(), w, pts)
+    # the label NUMBERING of the two paths may differ (canonical relabelling): the metrics do not depend on it
+    assert abs(out["s_iou"] - o[0]) < 1e-12 and abs(out["s_recall"] - o[4]) < 1e-12
+    params, status, seg_type = drv.stage2_fits(pts, nrm, lab, typ)
+    assert (status[: int(lab.max()) + 1] == 0).all()
