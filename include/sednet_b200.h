@@ -4,7 +4,7 @@
  *
  * The reference (yuanqili78/SED-Net) has no FFI: its boundary for this path is a set of Python functions and
  * nn.Module methods.  Every entry point below names the reference function (file:line under the reference
- * root) it stands in for; the Python mirror of those functions (sed-net_b200/src/*.py) binds these symbols
+ * root) it stands in for; the Python mirror of those functions (the .py files of sed-net_b200/src) binds these symbols
  * through ctypes, see INTEGRATION.md.
  *
  * Conventions

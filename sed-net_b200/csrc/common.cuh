@@ -1,5 +1,6 @@
 // Shared device helpers for the sm_100a kernels of the SED-Net hot path.
 #pragma once
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -8,8 +9,9 @@
 #define SED_ERR_UNSUPPORTED (-2)
 #define SED_ERR_CUDA_BASE (-1000)  // -(1000 + cudaError_t)
 
-// counts kernel launches issued by the library (sed_launch_count)
-extern long long g_sed_launches;
+// counts kernel launches issued by the library (sed_launch_count); atomic: the entry points may be called from
+// several host threads
+extern std::atomic<long long> g_sed_launches;
 
 #define SED_CHECK_LAUNCH()                                   \
     do {                                                     \

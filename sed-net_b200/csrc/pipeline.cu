@@ -7,7 +7,7 @@
 
 #include "internal.h"
 
-long long g_sed_launches = 0;
+std::atomic<long long> g_sed_launches{0};
 
 namespace sed {
 
@@ -100,9 +100,7 @@ const char* sed_error_string(int code) {
 }
 
 int64_t sed_launch_count(int reset) {
-    const long long v = g_sed_launches;
-    if (reset) g_sed_launches = 0;
-    return v;
+    return reset ? g_sed_launches.exchange(0) : g_sed_launches.load();
 }
 
 void sed_pipeline_destroy(sed_pipeline_t* p) {
