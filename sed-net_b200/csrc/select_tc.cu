@@ -893,10 +893,11 @@ static int launch_stream(const CUtensorMap& xh, const CUtensorMap& xl, const __h
 // row, K up to KS_KMAX.  Same single-pass scheme as the kNN kernel above, for 128-channel rows: the query tile (hi and
 // lo parts) lives in TMEM for the whole CTA (A operand from TMEM), which leaves shared memory to three 32 KB candidate
 // stages and 252-entry row buffers; only the scores are kept (no indices).
-constexpr int KS_CAP = 252;       // 1008-B row stride: LDS.128 conflict-free
+constexpr int KS_CAP = 316;       // 1264-B row stride: LDS.128 conflict-free (prunes dominate this kernel: buffers as large as shared memory allows)
 constexpr int KS_KMAX = 200;
 constexpr int KS_WIN = 12;
-constexpr int KS_STAGES = 3;
+constexpr int KS_SOFT = 252;       // soft mark of the CTA-wide booked prunes (0 = off; SEDNET_B200_KS_SOFT; swept on the GPU)
+constexpr int KS_STAGES = 2;       // the MMA (768 cycles per tile) paces the stream: two candidate stages suffice
 constexpr int KS_NBUF = 3;        // TMEM: 3 x 128 accumulator columns + 128 columns of Q
 constexpr uint32_t KS_XPART = 2 * SS_XPART;              // 64 rows x 128 channels fp16 (two 64-channel boxes)
 
@@ -919,12 +920,14 @@ kth_stream_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
     const uint32_t bar_s_full = bar_x_empty + 8 * KS_STAGES;   // [KS_NBUF]
     const uint32_t bar_s_empty = bar_s_full + 8 * KS_NBUF;     // [KS_NBUF]
     const uint32_t tmem_slot = bar_s_empty + 8 * KS_NBUF;
+    const uint32_t sched_addr = tmem_slot + 8;                 // [16] tile index of a booked CTA-wide prune (as in the kNN kernel)
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.y, q0 = blockIdx.x * ST_M;
     const int Nc = p.Nc;
     const int T = (Nc + SS_NC - 1) / SS_NC;
+    if (threadIdx.x < 16) sts_u32(sched_addr + threadIdx.x * 4, 0xffffffffu);
 
     if (threadIdx.x == 0) {
         mbar_init(bar_q_full, 128);
@@ -1044,6 +1047,17 @@ kth_stream_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
             tmem_ld_wait();
             tmem_ld32(sb + 32, b0);
             tmem_ld32(sb + 64 + 32, b1);
+            // CTA-wide booked prunes (see select_stream_kernel): the four warps share the TMEM ring, so they prune together
+            if (p.soft > 0) {
+                if (lds_u32(sched_addr + (uint32_t)(j & 15) * 4u) == (uint32_t)j) {
+                    ss_prune<false>(key_addr, 0u, KS_CAP, k, p.win, cnt, thr);
+                } else if (__any_sync(0xffffffffu, cnt > p.soft)) {
+                    bool booked = false;
+#pragma unroll
+                    for (int d = 1; d <= SS_LAG; ++d) booked |= lds_u32(sched_addr + (uint32_t)((j + d) & 15) * 4u) == (uint32_t)(j + d);
+                    if (!booked && lane == 0) sts_u32(sched_addr + (uint32_t)((j + SS_LAG) & 15) * 4u, (uint32_t)(j + SS_LAG));
+                }
+            }
             maybe_prune();
             process(a0, a1, nvalid);
             tmem_ld_wait();
@@ -1236,9 +1250,9 @@ int cos_select_tc(const float* Q, const float* Cand, int B, int Nq, int Nc, cons
     if (rc == SED_OK) rc = make_map_f16(&mql, ql, B, Nq, 128);
     if (rc == SED_OK) rc = make_map_f16(&mch, ch, B, Nc, 128);
     if (rc == SED_OK) rc = make_map_f16(&mcl, cl, B, Nc, 128);
-    static const int ks_win = env_int("SEDNET_B200_KS_WIN", KS_WIN);
+    static const int ks_win = env_int("SEDNET_B200_KS_WIN", KS_WIN), ks_soft = env_int("SEDNET_B200_KS_SOFT", KS_SOFT);
     SelParams p{nullptr, nullptr, nullptr, nullptr, scale, Nq, Nc, 0, K, nc_ptr, 0.f, idx_out, idx64, kth_out, 0,
-                min(max(ks_win, 0), max(KS_CAP - 32 - K - 8, 0)), 0};
+                min(max(ks_win, 0), max(KS_CAP - 32 - K - 8, 0)), ks_soft > 0 ? min(max(ks_soft, K + 16), KS_CAP - 33) : 0};
     static const bool radix = [] { const char* e = getenv("SEDNET_B200_KNN"); return e && !strcmp(e, "radix"); }();
     if (rc == SED_OK && kth_out && K <= KS_KMAX && !radix) {
         CUtensorMap xh64, xl64;   // 64-row candidate tiles
