@@ -430,9 +430,10 @@ def test_knn_heavy_ties(dev):
     assert sorted(zero) == list(np.flatnonzero(rep == rep[r]))
 
 
-@pytest.mark.parametrize("quantile", [0.015, 0.0262])
+@pytest.mark.parametrize("quantile", [0.015, 0.02, 0.0262])
 def test_bandwidth_streaming_and_fallback(dev, quantile):
-    """K = int(quantile * 10000) = 150 runs the streaming K-th-score kernel, 262 the multi-pass radix select."""
+    """K = int(quantile * 10000) = 150 and 200 (its upper limit) run the streaming K-th-score kernel, 262 the multi-pass
+    radix select."""
     from sednet_b200.src.mean_shift import MeanShift
     _, _, lab, _, _ = synth.make_cloud(31, 3000, n_patches=7, min_pts=300)
     X = t(synth.make_embedding(lab, 128, 0.03, 9))
