@@ -301,3 +301,61 @@ def test_config1_single_cloud_2048(dev):
         want = np.concatenate([ra.numpy().ravel(), [float(rd)]])
         got = got if got[:3] @ want[:3] > 0 else -got
         assert rel_err(got, want) < 1e-4
+
+
+@pytest.mark.parametrize("N", [64, 65, 127, 128, 129, 1000, 4097])
+def test_knn_shape_sweep_exactness(dev, N):
+    """Tile-boundary sizes, channel counts from 1 to 64 and k from 1 to 64 (k <= N): every returned list is the k nearest
+    in FP64 (up to the FP32 cancellation noise of the reference's own Gram form), self first, no duplicates; and the
+    point x normal metric on the same sizes."""
+    from sednet_b200.src import PointNet
+    rng = np.random.default_rng(N)
+    for C, k in ((1, 1), (3, 5), (17, min(40, N)), (64, min(64, N))):
+        x = rng.normal(size=(2, C, N)).astype(np.float32) * (10.0 if C == 17 else 1.0)
+        idx = PointNet.knn(t(x).to(dev), k, k).cpu().numpy()
+        assert idx.shape == (2, N, k) and idx.min() >= 0 and idx.max() < N
+        for b in range(2):
+            xd = x[b].astype(np.float64)
+            xx = (xd * xd).sum(0)
+            for r in rng.choice(N, min(N, 16), replace=False):
+                d = ((xd - xd[:, r:r + 1]) ** 2).sum(0)
+                kth = np.partition(d, k - 1)[k - 1]
+                tol = 8 * np.finfo(np.float32).eps * (xx[r] + xx.max())
+                assert d[idx[b, r]].max() <= kth + tol and len(set(idx[b, r])) == k
+                assert d[idx[b, r, 0]] <= tol                      # the point itself (or an exact duplicate) comes first
+    p, nrm, _, _, _ = synth.make_cloud(N, max(N, 200), n_patches=1, min_pts=max(N, 200))
+    x6 = np.concatenate([p[:N], nrm[:N]], 1).T[None].copy()
+    k = min(20, N)
+    idx = PointNet.knn_points_normals(t(x6).to(dev), k, k, 1.0).cpu().numpy()[0]
+    for r in rng.choice(N, 16, replace=False):
+        d = _pn_metric_fp64(x6[0], r)
+        assert d[idx[r]].max() <= np.partition(d, k - 1)[k - 1] * (1 + 1e-5) + 1e-7 and len(set(idx[r])) == k
+
+
+def test_stage2_and_three_nn_edge_shapes(dev):
+    """three_nn with fewer than three known points and n != m; stage-2 fits on a segment just at the 20-point minimum."""
+    from sednet_b200.Fitting_patches_and_edges.pointnet2.pointnet2_utils import three_nn
+    from sednet_b200.Fitting_patches_and_edges.primitive_forward_v2 import fit_segments_batched_v2
+    import oracle_v2 as O2
+    rng = np.random.default_rng(0)
+    unknown, known = rng.normal(size=(1, 37, 3)).astype(np.float32), rng.normal(size=(1, 2, 3)).astype(np.float32)
+    dist, idx = three_nn(t(unknown).to(dev), t(known).to(dev))
+    d2 = ((unknown[0][:, None] - known[0][None]) ** 2).sum(-1)
+    assert np.array_equal(idx[0, :, :2].cpu().numpy(), np.argsort(d2, 1, kind="stable"))
+    assert bool(torch.isinf(dist[0, :, 2]).all())                      # the third slot stays at the reference's 1e40 -> inf
+    for n, m in ((1, 5), (130, 1025), (2049, 7)):
+        u, kn = rng.normal(size=(1, n, 3)).astype(np.float32), rng.normal(size=(1, m, 3)).astype(np.float32)
+        dist, idx = three_nn(t(u).to(dev), t(kn).to(dev))
+        rd, ri = O2.three_nn(u[0], kn[0])
+        assert (idx[0].cpu().numpy() == ri).mean() > 0.999 and np.abs(dist[0].cpu().numpy() - np.sqrt(rd)).max() < 1e-6
+    # 20 points of a plane + 19 points of a sphere: the first is fitted, the second skipped (:953)
+    pl = np.concatenate([rng.uniform(-1, 1, (20, 2)), np.zeros((20, 1))], 1).astype(np.float32)
+    sp = rng.normal(size=(19, 3)); sp = (sp / np.linalg.norm(sp, axis=1, keepdims=True)).astype(np.float32)
+    pts = np.concatenate([pl, sp])[None]
+    nrm = np.concatenate([np.tile([[0, 0, 1.0]], (20, 1)), sp]).astype(np.float32)[None]
+    lab = np.concatenate([np.zeros(20), np.ones(19)]).astype(np.int64)[None]
+    params, status = fit_segments_batched_v2(t(pts).to(dev), t(nrm).to(dev), t(lab).to(dev),
+                                             t(np.array([[1, 5]], np.int32)).to(dev), plane_filter_ratio=0.5)
+    assert status.cpu().numpy().tolist() == [[0, 1]]
+    a = params[0, 0, :3].cpu().numpy()
+    assert abs(abs(a[2]) - 1) < 1e-6 and abs(float(params[0, 0, 3])) < 1e-6
