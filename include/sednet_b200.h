@@ -156,8 +156,8 @@ int sed_ms_bandwidth(const float* X, int B, int N, int d, int K, float min_bw, f
                      sed_stream_t stream);
 
 /* src/mean_shift.py:45-79 mean_shift_: `iterations` fixed shifts on the unit hypersphere.
- *   X (B,N,d), bw (B) device, kernel_type 0 gaussian / 1 epanechnikov, prec_mode 0 = FP32 FFMA (reference
- *   operation order), tcgen05 modes (d <= 128, zero-padded to 128 columns) with FP16 hi/lo split operands and FP32
+ *   X (B,N,d), d <= 256 a multiple of 4, bw (B) device, kernel_type 0 gaussian / 1 epanechnikov, prec_mode 0 = FP32 FFMA
+ *   (reference operation order; the only mode for d > 128, e.g. the 148-column hpnet embedding), tcgen05 modes (d <= 128, zero-padded to 128 columns) with FP16 hi/lo split operands and FP32
  *   accumulation:
  *   1 = S from 3 MMAs (Qh.Xh + Qh.Xl + Ql.Xh), O from 2 (Ph.Xh + Ph.Xl);  3 = S from 3, O from 1 (Ph.Xh);
  *   2 = single FP16 pass for both (fast, not FP32-faithful).
@@ -230,6 +230,13 @@ int sed_inst_edges(const int* idx3, const int64_t* insts, int n, int strict, uin
  * any neighbour gets the instance of the point nearest to its first point. */
 int sed_face_face_map(const float* points, const int64_t* insts, const int* idx3, const int64_t* primitive_ids, int n_ids,
                       int n, int nn_num_thresh, uint8_t* mat, sed_stream_t stream);
+
+/* ------------------------------------------------------------------ HPNet-style embedding weights */
+
+/* compute_entropy, src/smooth_normal_matrix.py:95-154: features (N,K) f32 -> out3 (device, 3 floats) =
+ * { E, average_dst, alpha }.  Only the first 5 * chunk points enter the pairwise sums (the reference's ITER = 5 chunks of
+ * CHUNK rows), which are divided by N * N as in the reference.  No host synchronisation. */
+int sed_compute_entropy(const float* features, int N, int K, int chunk, float* out3, sed_stream_t stream);
 
 /* ------------------------------------------------------------------ evaluation (src/segment_utils.py, src/utils.py) */
 

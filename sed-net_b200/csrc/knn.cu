@@ -424,7 +424,7 @@ static bool use_tc() {
 }
 
 int knn_l2(const float* x, long long bstride, int B, int C, int N, int k, void* idx, int idx64, cudaStream_t st, int sorted) {
-    if (!x || !idx || B <= 0 || C <= 0 || C > 128 || N < k || k <= 0) return SED_ERR_ARG;
+    if (!x || !idx || B <= 0 || C <= 0 || C > 256 || N < k || k <= 0) return SED_ERR_ARG;
     if (use_tc()) {
         const int rc = knn_tc(x, bstride, B, C, N, k, 0, 0.f, idx, idx64, st, sorted);
         if (rc != SED_ERR_UNSUPPORTED) return rc;
@@ -451,7 +451,7 @@ int knn_pn(const float* x6, long long bstride, int B, int N, int k, float W, voi
 // Q (B,Nq,d), Cand (B,Nc,d) row-major; nc_ptr optional per-cloud candidate count; out (B,Nq) int32/int64.
 int nearest_cos(const float* Q, const float* Cand, int B, int Nq, int Nc, const int* nc_ptr, int d, void* out,
                 int idx64, cudaStream_t st) {
-    if (!Q || !Cand || !out || B <= 0 || d <= 0 || d > 128 || (d & 3) || Nq <= 0 || Nc <= 0) return SED_ERR_ARG;
+    if (!Q || !Cand || !out || B <= 0 || d <= 0 || d > 256 || (d & 3) || Nq <= 0 || Nc <= 0) return SED_ERR_ARG;
     if (use_tc()) {
         const int rc = cos_select_tc(Q, Cand, B, Nq, Nc, nc_ptr, d, 1, nullptr, out, idx64, st);
         if (rc != SED_ERR_UNSUPPORTED) return rc;
@@ -479,7 +479,7 @@ int sed_knn_pn(const float* x6, int B, int N, int k, float W, void* idx, int idx
 int sed_ms_bandwidth(const float* X, int B, int N, int d, int K, float min_bw, float* kth_ws, float* bw,
                      sed_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!X || !kth_ws || !bw || B <= 0 || d <= 0 || d > 128 || (d & 3) || K <= 0 || N < K) return SED_ERR_ARG;
+    if (!X || !kth_ws || !bw || B <= 0 || d <= 0 || d > 256 || (d & 3) || K <= 0 || N < K) return SED_ERR_ARG;
     KnnParams p{};
     p.xq = p.xc = X; p.q_bstride = p.c_bstride = (long long)N * d; p.ldq = p.ldc = d;
     p.C = d; p.Nq = p.Nc = N; p.k = K; p.W = 0.f; p.out_idx = nullptr; p.idx64 = 0; p.out_kth = kth_ws;

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) transpose_rows_kernel(const float* __rest
 // ------------------------------------------------------------------------------------------------ shift (FFMA)
 constexpr int MS_TQ = 64;   // query rows per CTA
 constexpr int MS_TK = 64;   // keys per tile
-constexpr int MS_D = 128;   // padded channel count
+constexpr int MS_DMAX = 256;   // widest embedding of the FFMA path (rows padded to 128 or 256 channels)
 constexpr int MS_THREADS = 256;
 
 struct ShiftParams {
@@ -70,12 +70,15 @@ __device__ __forceinline__ float ms_kernel_weight(float dot, float b2, int kerne
     return fmaxf(__fmul_rn(0.75f, __fsub_rn(1.0f, __fdiv_rn(dist, b2))), 0.f);
 }
 
+// D: padded channel count (128, or 256 for embeddings wider than 128: the hpnet spectral embedding has 148 columns)
+template <int D>
 __global__ void __launch_bounds__(MS_THREADS, 1) ms_shift_ffma_kernel(ShiftParams p) {
+    constexpr int G = D / 64;   // float4 channel groups per thread: channels g * 64 + tx * 4 + [0,4)
     extern __shared__ __align__(16) float sm[];
-    float* Qt = sm;                         // [128][64]   Qt[c][q]
-    float* Xt = Qt + MS_D * MS_TQ;          // [128][64]   Xt[c][key]
-    float* Xr = Xt + MS_D * MS_TK;          // [64][128]   Xr[key][c]
-    float* Ps = Xr + MS_TK * MS_D;          // [64][64]    Ps[key][q], q-quads swizzled by key
+    float* Qt = sm;                         // [D][64]     Qt[c][q]
+    float* Xt = Qt + D * MS_TQ;          // [D][64]     Xt[c][key]
+    float* Xr = Xt + D * MS_TK;          // [64][D]     Xr[key][c]
+    float* Ps = Xr + MS_TK * D;          // [64][64]    Ps[key][q], q-quads swizzled by key
 
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int b = blockIdx.y, q0 = blockIdx.x * MS_TQ;
@@ -87,7 +90,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_shift_ffma_kernel(ShiftParam
     const float b2 = __fmul_rn(bwv, bwv);
 
     // ---- stage the query tile transposed: thread -> (row, channel quad)
-    for (int e = tid; e < MS_TQ * (MS_D / 4); e += MS_THREADS) {
+    for (int e = tid; e < MS_TQ * (D / 4); e += MS_THREADS) {
         const int r = e & 63, c4 = e >> 6;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (q0 + r < N && c4 * 4 < d) v = __ldg(reinterpret_cast<const float4*>(Q + (long long)(q0 + r) * d + c4 * 4));
@@ -97,13 +100,13 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_shift_ffma_kernel(ShiftParam
         Qt[(c4 * 4 + 3) * MS_TQ + r] = v.w;
     }
 
-    float o[4][8];
+    float o[4][4 * G];
     float l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         l[i] = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[i][e] = 0.f;
+        for (int e = 0; e < 4 * G; ++e) o[i][e] = 0.f;
     }
 
     const int ntiles = (N + MS_TK - 1) / MS_TK;
@@ -111,13 +114,13 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_shift_ffma_kernel(ShiftParam
         const int j0 = t * MS_TK;
         __syncthreads();  // previous tile fully consumed (and Qt visible on the first pass)
         // ---- load the key tile in both layouts (coalesced from X and XT)
-        for (int e = tid; e < MS_TK * (MS_D / 4); e += MS_THREADS) {
-            const int r = e >> 5, c4 = e & 31;   // row-major: 32 quads per row
+        for (int e = tid; e < MS_TK * (D / 4); e += MS_THREADS) {
+            const int r = e / (D / 4), c4 = e % (D / 4);   // row-major: D / 4 quads per row
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j0 + r < N && c4 * 4 < d) v = __ldg(reinterpret_cast<const float4*>(X + (long long)(j0 + r) * d + c4 * 4));
-            *reinterpret_cast<float4*>(Xr + r * MS_D + c4 * 4) = v;
+            *reinterpret_cast<float4*>(Xr + r * D + c4 * 4) = v;
         }
-        for (int e = tid; e < MS_D * (MS_TK / 4); e += MS_THREADS) {
+        for (int e = tid; e < D * (MS_TK / 4); e += MS_THREADS) {
             const int c = e >> 4, k4 = e & 15;   // channel-major: 16 quads per channel row
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < d) {
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_shift_ffma_kernel(ShiftParam
 #pragma unroll
             for (int e = 0; e < 4; ++e) s[i][e] = 0.f;
 #pragma unroll 8
-        for (int c = 0; c < MS_D; ++c) {
+        for (int c = 0; c < D; ++c) {
             const float4 a = *reinterpret_cast<const float4*>(Qt + c * MS_TQ + ty * 4);
             const float4 k4 = *reinterpret_cast<const float4*>(Xt + c * MS_TK + tx * 4);
             const float aa[4] = {a.x, a.y, a.z, a.w};
@@ -166,19 +169,21 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_shift_ffma_kernel(ShiftParam
             *reinterpret_cast<float4*>(Ps + key * MS_TQ + slot * 4) = make_float4(pv[0], pv[1], pv[2], pv[3]);
         }
         __syncthreads();
-        // ---- O += P . X : 4 queries x 8 channels per thread
+        // ---- O += P . X : 4 queries x 4 G channels per thread
 #pragma unroll 4
         for (int key = 0; key < MS_TK; ++key) {
             const int slot = ty ^ ((key >> 2) & 15);
             const float4 pq = *reinterpret_cast<const float4*>(Ps + key * MS_TQ + slot * 4);
-            const float4 x0 = *reinterpret_cast<const float4*>(Xr + key * MS_D + tx * 4);
-            const float4 x1 = *reinterpret_cast<const float4*>(Xr + key * MS_D + 64 + tx * 4);
             const float pp[4] = {pq.x, pq.y, pq.z, pq.w};
-            const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int g = 0; g < G; ++g) {
+                const float4 xg = *reinterpret_cast<const float4*>(Xr + key * D + g * 64 + tx * 4);
+                const float xx[4] = {xg.x, xg.y, xg.z, xg.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[i][e] = fmaf(pp[i], xx[e], o[i][e]);
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) o[i][g * 4 + e] = fmaf(pp[i], xx[e], o[i][g * 4 + e]);
+            }
         }
     }
 
@@ -190,11 +195,11 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_shift_ffma_kernel(ShiftParam
         for (int m = 8; m > 0; m >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, m);
         const float D = __fdiv_rn(1.0f, sum);
         const int ql = ty * 4 + i;
-        float z[8];
+        float z[4 * G];
         float nn = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c = (e < 4) ? (tx * 4 + e) : (64 + tx * 4 + e - 4);
+        for (int e = 0; e < 4 * G; ++e) {
+            const int c = (e >> 2) * 64 + tx * 4 + (e & 3);
             const float qv = Qt[c * MS_TQ + ql];
             const float M = __fsub_rn(__fmul_rn(o[i][e], D), qv);
             z[e] = __fadd_rn(qv, M);
@@ -206,9 +211,12 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_shift_ffma_kernel(ShiftParam
         const int q = q0 + ql;
         if (q < N) {
             float* dst = p.out + ((long long)b * N + q) * d;
-            const int c0 = tx * 4, c1 = 64 + tx * 4;
-            if (c0 < d) *reinterpret_cast<float4*>(dst + c0) = make_float4(z[0] / nrm, z[1] / nrm, z[2] / nrm, z[3] / nrm);
-            if (c1 < d) *reinterpret_cast<float4*>(dst + c1) = make_float4(z[4] / nrm, z[5] / nrm, z[6] / nrm, z[7] / nrm);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const int c = g * 64 + tx * 4;
+                if (c < d)
+                    *reinterpret_cast<float4*>(dst + c) = make_float4(z[g * 4] / nrm, z[g * 4 + 1] / nrm, z[g * 4 + 2] / nrm, z[g * 4 + 3] / nrm);
+            }
         }
     }
 }
@@ -216,10 +224,16 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_shift_ffma_kernel(ShiftParam
 int ms_shift_ffma(const float* X, const float* XT, const float* Q, const float* bw, int B, int N, int d,
                   int kernel_type, float* out, cudaStream_t st) {
     ShiftParams p{X, XT, Q, bw, out, N, d, kernel_type};
-    const size_t smem = (size_t)(MS_D * MS_TQ + MS_D * MS_TK + MS_TK * MS_D + MS_TK * MS_TQ) * sizeof(float);
-    SED_CUDA(cudaFuncSetAttribute(ms_shift_ffma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int D = d <= 128 ? 128 : 256;
+    const size_t smem = (size_t)(D * MS_TQ + D * MS_TK + MS_TK * D + MS_TK * MS_TQ) * sizeof(float);
     dim3 grid((N + MS_TQ - 1) / MS_TQ, B);
-    ms_shift_ffma_kernel<<<grid, MS_THREADS, smem, st>>>(p);
+    if (D == 128) {
+        SED_CUDA(cudaFuncSetAttribute(ms_shift_ffma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ms_shift_ffma_kernel<128><<<grid, MS_THREADS, smem, st>>>(p);
+    } else {
+        SED_CUDA(cudaFuncSetAttribute(ms_shift_ffma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ms_shift_ffma_kernel<256><<<grid, MS_THREADS, smem, st>>>(p);
+    }
     SED_CHECK_LAUNCH();
     return SED_OK;
 }
@@ -292,14 +306,20 @@ __global__ void __launch_bounds__(256) nms_vote_kernel(const float* __restrict__
     const int* cb = counts + (long long)b * N;
     const int u = ub[ui];
     const float bwv = bw[b];
-    float4 cu = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane * 4 < d) cu = __ldg(reinterpret_cast<const float4*>(Cb + (long long)u * d + lane * 4));
+    float4 cu[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};   // d <= 256: two quads per lane
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+        if (h * 128 + lane * 4 < d) cu[h] = __ldg(reinterpret_cast<const float4*>(Cb + (long long)u * d + h * 128 + lane * 4));
     int best_v = 0, best_j = 0;
     for (int t = 0; t < U; ++t) {
         const int j = ub[t];
-        float4 cj = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane * 4 < d) cj = __ldg(reinterpret_cast<const float4*>(Cb + (long long)j * d + lane * 4));
-        float dot = fmaf(cu.x, cj.x, fmaf(cu.y, cj.y, fmaf(cu.z, cj.z, cu.w * cj.w)));
+        float dot = 0.f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float4 cj = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (h * 128 + lane * 4 < d) cj = __ldg(reinterpret_cast<const float4*>(Cb + (long long)j * d + h * 128 + lane * 4));
+            dot += fmaf(cu[h].x, cj.x, fmaf(cu[h].y, cj.y, fmaf(cu[h].z, cj.z, cu[h].w * cj.w)));
+        }
         dot = warp_sum_f(dot);
         const float dist = __fsub_rn(2.0f, __fmul_rn(2.0f, dot));
         const int v = (dist < bwv) ? cb[j] : 0;
@@ -378,7 +398,7 @@ int sed_normalize_transpose(const float* emb, int B, int d, int N, float* X, sed
 int sed_ms_shift(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type, int prec_mode,
                  float* out, float* tmp, sed_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!X || !bw || !out || !tmp || B <= 0 || N <= 0 || d <= 0 || d > MS_D || (d & 3) || iterations < 0)
+    if (!X || !bw || !out || !tmp || B <= 0 || N <= 0 || d <= 0 || d > MS_DMAX || (d & 3) || iterations < 0)
         return SED_ERR_ARG;
     if (kernel_type != 0 && kernel_type != 1) return SED_ERR_ARG;
     if (iterations == 0) {
@@ -423,7 +443,7 @@ int sed_ms_nms(const float* centers, const float* X, const float* bw, int B, int
                sed_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!centers || !X || !bw || !labels || !center_ids || !n_centers || !centers_out || !workspace) return SED_ERR_ARG;
-    if (B <= 0 || N <= 0 || d <= 0 || d > 128 || (d & 3) || max_centers <= 0) return SED_ERR_ARG;
+    if (B <= 0 || N <= 0 || d <= 0 || d > MS_DMAX || (d & 3) || max_centers <= 0) return SED_ERR_ARG;
     Arena A(workspace, sed_ms_nms_workspace_bytes(B, N));
     NmsWs w;
     carve_nms(A, B, N, w);

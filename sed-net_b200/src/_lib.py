@@ -41,6 +41,7 @@ SIGNATURES = {
     "sed_three_nn": (I, [c_f32p, c_f32p, I, I, I, c_f32p, c_i32p, c_vp]),
     "sed_inst_edges": (I, [c_i32p, c_i64p, I, I, c_vp, c_vp]),
     "sed_face_face_map": (I, [c_f32p, c_i64p, c_i32p, c_i64p, I, I, I, c_vp, c_vp]),
+    "sed_compute_entropy": (I, [c_f32p, I, I, I, c_f32p, c_vp]),
     "sed_segment_tables": (I, [c_i64p, c_i64p, c_i64p, c_i64p, I, I, I, I, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
                                c_vp]),
     "sed_type_vote_weighted": (I, [c_i64p, c_f32p, I, I, I, c_f32p, c_vp]),

@@ -1,0 +1,75 @@
+"""GPU parity of the deterministic part of hpnet_process: compute_entropy and the cache-hit branch
+against the values recorded from the unmodified reference (tests/golden/hpnet.npz), and mean-shift on the resulting
+148-column embedding against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import oracle_hpnet as OH
+from conftest import ROOT
+from util import canon
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from sednet_b200.src import _lib
+    _lib.load()
+    return torch.device("cuda", 0)
+
+
+def test_compute_entropy_and_hpnet_golden(dev, tmp_path):
+    from sednet_b200.src import smooth_normal_matrix as snm
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hpnet.npz"))
+    for case in (0, 1):
+        seed, n, chunk = [int(v) for v in g[f"c{case}_cfg"]]
+        feat, v, types, edges = OH.hpnet_case(seed, n)
+        e_feat = float(snm.compute_entropy(feat.to(dev), CHUNK=chunk))
+        e_v = float(snm.compute_entropy(v.to(dev), CHUNK=chunk))
+        # FP32 sums of 4e6 terms in the reference (torch.sum per chunk pair), FP64 here: 1e-5 relative
+        assert abs(e_feat - g[f"c{case}_ent"][0]) < 1e-5 * g[f"c{case}_ent"][0], (e_feat, g[f"c{case}_ent"])
+        assert abs(e_v - g[f"c{case}_ent"][1]) < 1e-5 * g[f"c{case}_ent"][1]
+        # cache-hit branch: the reference's file names, in a scratch working directory
+        cache = tmp_path / f"c{case}" / "src" / "normal_smooth_cache"
+        cache.mkdir(parents=True)
+        torch.save(v, str(cache / "Us_7_0.1_50.pt"))
+        torch.save(torch.tensor(float(g[f"c{case}_ent"][1])), str(cache / "WUs_7_0.1_50.pt"))
+        cwd = os.getcwd()
+        os.chdir(str(tmp_path / f"c{case}"))
+        try:
+            emb = snm.hpnet_process(feat.to(dev), torch.zeros(1, n, 3, device=dev), torch.zeros(1, n, 3, device=dev), id=7,
+                                    types=types.to(dev), edges=edges.to(dev), normal_smooth_w=0.5, CHUNK=chunk)
+        finally:
+            os.chdir(cwd)
+        assert emb.shape == (1, n, 148)
+        ref = g[f"c{case}_emb_sample"]
+        assert np.abs(emb[0, ::50].cpu().numpy() - ref).max() < 2e-5 * np.abs(ref).max()
+        assert abs(float(emb.double().sum()) - float(g[f"c{case}_emb_sum"])) < 1e-4 * abs(float(g[f"c{case}_emb_sum"]))
+    with pytest.raises(NotImplementedError):
+        snm.hpnet_process(feat.to(dev), None, None, id=None)            # no cache, no v: the lobpcg branch is not built
+    with torch.no_grad():
+        e_o = float(OH.compute_entropy(types.exp(), CHUNK=chunk))
+    assert abs(float(snm.compute_entropy(types.exp().to(dev), CHUNK=chunk)) - e_o) < 1e-5 * e_o     # K = 6
+
+
+def test_meanshift_on_148_column_embedding(dev):
+    """The driver's flow after hpnet_process (generate_predictions_aug.py:371-384): L2-normalise the 148-column embedding
+    and cluster it.  Rows wider than 128 run on the FFMA kernels (bandwidth, shift, nms): labels, bandwidth and shifted
+    points against the oracle."""
+    from sednet_b200.src.mean_shift import MeanShift
+    feat, v, types, edges = OH.hpnet_case(5, 3000)
+    with torch.no_grad():
+        emb = OH.hpnet_combine(feat, v, torch.tensor(0.3), types, edges, 0.5, 600)
+        X = torch.nn.functional.normalize(emb[0], p=2, dim=1).contiguous()
+        rX, rc, rbw, rlab = O.mean_shift(X, 10000, 0.015, 20)
+    ms = MeanShift()
+    assert X.shape[1] == 148 and ms._mode(148) == 0
+    newX, center, bw, labels = ms.mean_shift(X.to(dev), 10000, 0.015, 20)
+    assert (canon(labels.cpu().numpy()) == canon(rlab.numpy())).all()
+    assert abs(float(bw) - float(rbw)) < 1e-4 * float(rbw)
+    assert float((newX.cpu() - rX).abs().max()) < 1e-4 and center.shape == rc.shape

@@ -127,3 +127,16 @@ def test_metrics_oracle_matches_reference():
         assert abs(float(OM.compute_type_miou_abc(logits[0], typ_gt.copy(), pred.copy(), I_gt)) - float(g[f"c{case}_abc"])) < 1e-7
         cd = OM.chamfer_distance(pts[pred == 0], pts[gt == 1])
         assert abs(cd - float(g[f"c{case}_cd"])) < 1e-7 * max(1.0, float(g[f"c{case}_cd"]))
+
+
+def test_hpnet_oracle_matches_reference():
+    """oracle/oracle_hpnet.py (compute_entropy, hpnet_process cache-hit branch) against the recorded reference values."""
+    import oracle_hpnet as OH
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hpnet.npz"))
+    seed, n, chunk = [int(v) for v in g["c0_cfg"]]
+    feat, v, types, edges = OH.hpnet_case(seed, n)
+    with torch.no_grad():
+        e = [float(OH.compute_entropy(x, CHUNK=chunk)) for x in (feat, v)]
+        emb = OH.hpnet_combine(feat, v, torch.tensor(float(g["c0_ent"][1])), types, edges, 0.5, chunk)
+    assert np.allclose(e, g["c0_ent"], rtol=1e-6, atol=0)
+    assert emb.shape == (1, n, 148) and np.abs(emb[0, ::50].numpy() - g["c0_emb_sample"]).max() < 1e-6
