@@ -224,12 +224,15 @@ __global__ void __launch_bounds__(MS_THREADS, 1) ms_shift_ffma_kernel(ShiftParam
 int ms_shift_ffma(const float* X, const float* XT, const float* Q, const float* bw, int B, int N, int d,
                   int kernel_type, float* out, cudaStream_t st) {
     ShiftParams p{X, XT, Q, bw, out, N, d, kernel_type};
-    const int D = d <= 128 ? 128 : 256;
+    const int D = d <= 128 ? 128 : (d <= 192 ? 192 : 256);
     const size_t smem = (size_t)(D * MS_TQ + D * MS_TK + MS_TK * D + MS_TK * MS_TQ) * sizeof(float);
     dim3 grid((N + MS_TQ - 1) / MS_TQ, B);
     if (D == 128) {
         SED_CUDA(cudaFuncSetAttribute(ms_shift_ffma_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ms_shift_ffma_kernel<128><<<grid, MS_THREADS, smem, st>>>(p);
+    } else if (D == 192) {   // the 148-column hpnet embedding
+        SED_CUDA(cudaFuncSetAttribute(ms_shift_ffma_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ms_shift_ffma_kernel<192><<<grid, MS_THREADS, smem, st>>>(p);
     } else {
         SED_CUDA(cudaFuncSetAttribute(ms_shift_ffma_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ms_shift_ffma_kernel<256><<<grid, MS_THREADS, smem, st>>>(p);
