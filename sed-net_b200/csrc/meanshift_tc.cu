@@ -395,10 +395,14 @@ static int launch_tc(const CUtensorMap& xh, const CUtensorMap& xl, const TcParam
     return p.kernel_type == 0 ? launch_tc_k<NS, NV, 0>(xh, xl, p, B, st) : launch_tc_k<NS, NV, 1>(xh, xl, p, B, st);
 }
 
+int ms_shift_tc192(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type, float* out,
+                   cudaStream_t st);   // meanshift_tc192.cu
+
 int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type, int prec_mode,
                 float* out, float* tmp, cudaStream_t st) {
     (void)tmp;
-    if (d > TC_D || d <= 0 || (d & 3)) return SED_ERR_UNSUPPORTED;
+    if (d > TC_D) return ms_shift_tc192(X, bw, B, N, d, iterations, kernel_type, out, st);   // 129..192 columns
+    if (d <= 0 || (d & 3)) return SED_ERR_UNSUPPORTED;
     const bool padded = d < TC_D;      // the kernel works on 128-wide rows: pad with zero columns, strip them at the end
     const bool has_lo = (prec_mode == 1 || prec_mode == 3);
     const size_t elems = (size_t)B * N * TC_D;

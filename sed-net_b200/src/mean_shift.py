@@ -13,7 +13,7 @@ class MeanShift:
     def __init__(self, prec_mode=None):
         """prec_mode of sed_ms_shift (include/sednet_b200.h): 0 FP32 FFMA, 1 / 3 tcgen05 FP16 hi/lo split (3+2 / 3+1 MMAs),
         2 plain FP16; None = $SEDNET_B200_MS_PREC if set, otherwise automatic: the FP32-faithful tensor-core mode 3
-        (embeddings up to 128 wide, zero-padded; identical labels, <= 4e-6 from mode 0), else the FFMA kernel."""
+        (embeddings up to 192 wide, zero-padded to 128 or 192; identical labels, <= 4e-6 from mode 0), else the FFMA kernel."""
         import os
         env = os.environ.get("SEDNET_B200_MS_PREC")
         self.prec_mode = prec_mode if prec_mode is not None else (int(env) if env is not None else None)
@@ -21,7 +21,7 @@ class MeanShift:
     def _mode(self, d):
         if self.prec_mode is not None:
             return self.prec_mode
-        return 3 if d <= 128 and d % 4 == 0 else 0
+        return 3 if d <= 192 and d % 4 == 0 else 0
 
     # -- src/mean_shift.py:19-43
     def mean_shift(self, X, num_samples, quantile, iterations, kernel_type="gaussian", bw=None, nms=True):

@@ -67,9 +67,20 @@ def test_meanshift_on_148_column_embedding(dev):
         emb = OH.hpnet_combine(feat, v, torch.tensor(0.3), types, edges, 0.5, 600)
         X = torch.nn.functional.normalize(emb[0], p=2, dim=1).contiguous()
         rX, rc, rbw, rlab = O.mean_shift(X, 10000, 0.015, 20)
-    ms = MeanShift()
-    assert X.shape[1] == 148 and ms._mode(148) == 0
-    newX, center, bw, labels = ms.mean_shift(X.to(dev), 10000, 0.015, 20)
-    assert (canon(labels.cpu().numpy()) == canon(rlab.numpy())).all()
-    assert abs(float(bw) - float(rbw)) < 1e-4 * float(rbw)
-    assert float((newX.cpu() - rX).abs().max()) < 1e-4 and center.shape == rc.shape
+    assert X.shape[1] == 148 and MeanShift()._mode(148) == 3 and MeanShift()._mode(200) == 0
+    for mode in (0, 3):                   # FFMA kernel (rows padded to 192), 192-wide tensor-core kernel
+        newX, center, bw, labels = MeanShift(prec_mode=mode).mean_shift(X.to(dev), 10000, 0.015, 20)
+        assert (canon(labels.cpu().numpy()) == canon(rlab.numpy())).all(), mode
+        assert abs(float(bw) - float(rbw)) < 1e-4 * float(rbw)
+        assert float((newX.cpu() - rX).abs().max()) < 1e-4 and center.shape == rc.shape, mode
+        assert float((torch.linalg.norm(newX, dim=1) - 1).abs().max()) < 1e-5
+    # epanechnikov kernel, tight planted clusters, a point count that is no multiple of the 128-row tiles
+    from sednet_b200 import synth
+    _, _, lab, _, _ = synth.make_cloud(2403, 2777, n_patches=6, min_pts=170)
+    Xe = torch.from_numpy(synth.make_embedding(lab, 148, 0.01, 3))
+    with torch.no_grad():
+        onew, _, _, olab = O.mean_shift(Xe, 10000, 0.015, 20, "epa")
+    for mode in (0, 3):
+        newX, _, _, labels = MeanShift(prec_mode=mode).mean_shift(Xe.to(dev), 10000, 0.015, 20, kernel_type="epa")
+        assert float((newX.cpu() - onew).abs().max()) < 1e-4, mode
+        assert (canon(labels.cpu().numpy()) == canon(olab.numpy())).all() and (canon(olab.numpy()) == canon(lab)).all()
