@@ -84,3 +84,24 @@ def test_meanshift_on_148_column_embedding(dev):
         newX, _, _, labels = MeanShift(prec_mode=mode).mean_shift(Xe.to(dev), 10000, 0.015, 20, kernel_type="epa")
         assert float((newX.cpu() - onew).abs().max()) < 1e-4, mode
         assert (canon(labels.cpu().numpy()) == canon(olab.numpy())).all() and (canon(olab.numpy()) == canon(lab)).all()
+
+
+@pytest.mark.parametrize("d,n", [(132, 300), (192, 129), (160, 1000)])
+def test_meanshift_tc192_edge_widths(dev, d, n):
+    """The 192-wide tensor-core kernel at the ends of its range (132 and 192 columns), with fewer points than one key
+    tile, one iteration and a batch of clouds with different bandwidths, against the FP32 FFMA kernel."""
+    import ctypes as C
+    from sednet_b200 import synth
+    from sednet_b200.src import _lib
+    B = 3
+    labs = [np.random.default_rng(s).integers(0, 4, n) for s in range(B)]
+    X = torch.stack([torch.from_numpy(synth.make_embedding(labs[b], d, 0.05, 7 + b)) for b in range(B)]).to(dev).contiguous()
+    bw = torch.tensor([0.3, 0.4, 0.5], device=dev)
+    for iters in (1, 6):
+        ref, got, tmp = torch.empty_like(X), torch.empty_like(X), torch.empty_like(X)
+        _lib.call("sed_ms_shift", _lib.ptr(X), _lib.ptr(bw), B, n, d, iters, 0, 0, _lib.ptr(ref), _lib.ptr(tmp), _lib.stream())
+        _lib.call("sed_ms_shift", _lib.ptr(X), _lib.ptr(bw), B, n, d, iters, 0, 3, _lib.ptr(got), _lib.ptr(tmp), _lib.stream())
+        # mode 3 drops the X_lo term of O (a 2^-12 relative rounding of X that averages out over a cluster: fewer than 100
+        # points per cluster here); the bar for shifted points is 1e-4 (DESIGN.md section 2)
+        assert float((got - ref).abs().max()) < 1e-4, (d, n, iters)
+        assert float((torch.linalg.norm(got, dim=2) - 1).abs().max()) < 1e-5
