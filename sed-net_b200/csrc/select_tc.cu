@@ -82,7 +82,7 @@ select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_consta
                  const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, SelParams p) {
     constexpr uint32_t PART_BYTES = KB * BOX_BYTES;
     constexpr uint32_t TILE2 = 2 * PART_BYTES;                     // hi + lo
-    constexpr int STAGES = (KB == 1) ? 3 : 2;
+    constexpr int STAGES = (KB == 1) ? 3 : (KB == 2 ? 2 : 1);   // KB = 3 (192-wide rows): one 96 KB candidate stage
     constexpr int NBINS = 1 << RBITS;
     constexpr int NPASS_RADIX = (OUT == OUT_TOP1) ? 0 : (32 + RBITS - 1) / RBITS;
     constexpr int NPASS = (OUT == OUT_TOP1) ? 1 : NPASS_RADIX + (OUT == OUT_IDX ? 1 : 0);
@@ -1145,30 +1145,32 @@ __global__ void pack_cm_kernel(const float* __restrict__ x, long long bstride, i
     xx[(long long)b * npad + n] = nrm;
 }
 
-// row-major x (B,N,d) d <= 128 -> fp16 hi/lo rows [B][N][128] scaled by `scale`
-__global__ void pack_rm_kernel(const float* __restrict__ x, long long rows, int d, float scale, __half* __restrict__ hi,
+// row-major x (B,N,d) d <= W -> fp16 hi/lo rows [B][N][W] (W = 128 or 192, zero-padded) scaled by `scale`
+__global__ void pack_rm_kernel(const float* __restrict__ x, long long rows, int d, int W, float scale, __half* __restrict__ hi,
                                __half* __restrict__ lo) {
     const long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (lane * 4 < d) v = *reinterpret_cast<const float4*>(x + row * d + lane * 4);
-    const float a[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
-    __align__(8) __half h[4];
-    __align__(8) __half l[4];
+    for (int c = lane * 4; c < W; c += 128) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < d) v = *reinterpret_cast<const float4*>(x + row * d + c);
+        const float a[4] = {v.x * scale, v.y * scale, v.z * scale, v.w * scale};
+        __align__(8) __half h[4];
+        __align__(8) __half l[4];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        h[e] = __float2half_rn(a[e]);
-        l[e] = __float2half_rn(a[e] - __half2float(h[e]));
+        for (int e = 0; e < 4; ++e) {
+            h[e] = __float2half_rn(a[e]);
+            l[e] = __float2half_rn(a[e] - __half2float(h[e]));
+        }
+        *reinterpret_cast<uint2*>(hi + row * W + c) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(lo + row * W + c) = *reinterpret_cast<const uint2*>(l);
     }
-    *reinterpret_cast<uint2*>(hi + row * 128 + lane * 4) = *reinterpret_cast<const uint2*>(h);
-    *reinterpret_cast<uint2*>(lo + row * 128 + lane * 4) = *reinterpret_cast<const uint2*>(l);
 }
 
 template <int MODE, int OUT, int KB, int RBITS>
 static int launch_select(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& xh, const CUtensorMap& xl,
                          const SelParams& p, int B, cudaStream_t st) {
-    constexpr int STAGES = (KB == 1) ? 3 : 2;
+    constexpr int STAGES = (KB == 1) ? 3 : (KB == 2 ? 2 : 1);   // KB = 3 (192-wide rows): one 96 KB candidate stage
     constexpr int NBINS = 1 << RBITS;
     constexpr size_t SEL = (OUT == OUT_TOP1) ? 1024 : (size_t)2 * NBINS * 128;
     constexpr size_t smem = (size_t)(STAGES + 1) * 2 * KB * BOX_BYTES + SEL + 1024 + 256;
@@ -1229,32 +1231,36 @@ int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn
 //   idx_out != null : index of the best candidate of every row (first on ties)       -> nms membership / labels
 int cos_select_tc(const float* Q, const float* Cand, int B, int Nq, int Nc, const int* nc_ptr, int d, int K,
                   float* kth_out, void* idx_out, int idx64, cudaStream_t st) {
-    if (d > 128 || (d & 3) || Nc >= 65536 || (kth_out && (K > Nc || K <= 0 || K > 255))) return SED_ERR_UNSUPPORTED;
+    if (d > 192 || (d & 3) || Nc >= 65536 || (kth_out && (K > Nc || K <= 0 || K > 255))) return SED_ERR_UNSUPPORTED;
+    const int W = d <= 128 ? 128 : 192;   // operand row width: two or three 64-channel boxes
     const bool same = (Q == Cand && Nq == Nc);
     const size_t rq = (size_t)B * Nq, rc_ = (size_t)B * Nc;
-    const size_t bytes_q = rq * 128 * sizeof(__half), bytes_c = rc_ * 128 * sizeof(__half);
+    const size_t bytes_q = rq * W * sizeof(__half), bytes_c = rc_ * W * sizeof(__half);
     ensure_pool_config();
     char* buf = nullptr;
     SED_CUDA(cudaMallocAsync((void**)&buf, 2 * bytes_q + (same ? 0 : 2 * bytes_c), st));
     __half *qh = (__half*)buf, *ql = (__half*)(buf + bytes_q);
     __half *ch = same ? qh : (__half*)(buf + 2 * bytes_q), *cl = same ? ql : (__half*)(buf + 2 * bytes_q + bytes_c);
     const float scale = 8.0f;
-    pack_rm_kernel<<<(unsigned)((rq + 7) / 8), 256, 0, st>>>(Q, (long long)rq, d, scale, qh, ql);
+    pack_rm_kernel<<<(unsigned)((rq + 7) / 8), 256, 0, st>>>(Q, (long long)rq, d, W, scale, qh, ql);
     ++g_sed_launches;
     if (!same) {
-        pack_rm_kernel<<<(unsigned)((rc_ + 7) / 8), 256, 0, st>>>(Cand, (long long)rc_, d, scale, ch, cl);
+        pack_rm_kernel<<<(unsigned)((rc_ + 7) / 8), 256, 0, st>>>(Cand, (long long)rc_, d, W, scale, ch, cl);
         ++g_sed_launches;
     }
     CUtensorMap mqh, mql, mch, mcl;
-    int rc = make_map_f16(&mqh, qh, B, Nq, 128);
-    if (rc == SED_OK) rc = make_map_f16(&mql, ql, B, Nq, 128);
-    if (rc == SED_OK) rc = make_map_f16(&mch, ch, B, Nc, 128);
-    if (rc == SED_OK) rc = make_map_f16(&mcl, cl, B, Nc, 128);
+    int rc = make_map_f16(&mqh, qh, B, Nq, W);
+    if (rc == SED_OK) rc = make_map_f16(&mql, ql, B, Nq, W);
+    if (rc == SED_OK) rc = make_map_f16(&mch, ch, B, Nc, W);
+    if (rc == SED_OK) rc = make_map_f16(&mcl, cl, B, Nc, W);
     static const int ks_win = env_int("SEDNET_B200_KS_WIN", KS_WIN), ks_soft = env_int("SEDNET_B200_KS_SOFT", KS_SOFT);
     SelParams p{nullptr, nullptr, nullptr, nullptr, scale, Nq, Nc, 0, K, nc_ptr, 0.f, idx_out, idx64, kth_out, 0,
                 min(max(ks_win, 0), max(KS_CAP - 32 - K - 8, 0)), ks_soft > 0 ? min(max(ks_soft, K + 16), KS_CAP - 33) : 0};
     static const bool radix = [] { const char* e = getenv("SEDNET_B200_KNN"); return e && !strcmp(e, "radix"); }();
-    if (rc == SED_OK && kth_out && K <= KS_KMAX && !radix) {
+    if (rc == SED_OK && W == 192) {   // 129..192 columns (the hpnet embedding): the multi-pass radix kernel, three boxes per row
+        rc = kth_out ? launch_select<SEL_COS, OUT_KTH, 3, 7>(mqh, mql, mch, mcl, p, B, st)
+                     : launch_select<SEL_COS, OUT_TOP1, 3, 8>(mqh, mql, mch, mcl, p, B, st);
+    } else if (rc == SED_OK && kth_out && K <= KS_KMAX && !radix) {
         CUtensorMap xh64, xl64;   // 64-row candidate tiles
         rc = make_map_f16(&xh64, ch, B, Nc, 128, SS_NC);
         if (rc == SED_OK) rc = make_map_f16(&xl64, cl, B, Nc, 128, SS_NC);
