@@ -39,15 +39,25 @@ def build_model(state, k=64):
     return m.cuda().eval()
 
 
-def predict_shape(model, model_inst, points_, normals_, labels, primitives_, quantile=0.015, iterations=50):
-    """points_, normals_ (1,N,3) float32 host tensors; labels, primitives_ (1,N) numpy ground truth.  Returns a dict."""
+def predict_shape(model, model_inst, points_, normals_, labels, primitives_, quantile=0.015, iterations=50,
+                  spectral_v=None, spectral_ent=None, normal_smooth_w=0.5, chunk=1000):
+    """points_, normals_ (1,N,3) float32 host tensors; labels, primitives_ (1,N) numpy ground truth.  With spectral_v
+    (1,N,12) -- the shape's cached normal-smoothness eigenvectors -- the embedding goes through hpnet_process first
+    (HPNet_embed = True, generate_predictions_aug.py:371-378).  Returns a dict."""
     points, normals = points_.cuda(), normals_.cuda()
     with torch.no_grad():
         _input = torch.cat([points, normals], 2)                                                   # :223
         primitives_log_prob = model(_input.permute(0, 2, 1), None, False)[1]                       # :224-226
         embedding, _, _, edges_pred = model_inst(_input.permute(0, 2, 1), None, False)             # :227-229
     pred_primitives = torch.max(primitives_log_prob[0], 0)[1].data.cpu().numpy()                   # :365
-    embedding = torch.nn.functional.normalize(embedding[0].T, p=2, dim=1)                          # :380
+    if spectral_v is not None:
+        from sednet_b200.src.smooth_normal_matrix import hpnet_process                             # src.smooth_normal_matrix
+        embedding = hpnet_process(embedding.transpose(1, 2), points, normals, types=primitives_log_prob.transpose(1, 2),
+                                  edges=edges_pred.transpose(1, 2), normal_smooth_w=normal_smooth_w, CHUNK=chunk,
+                                  v=spectral_v.cuda(), ent=spectral_ent)                            # :372-376
+        embedding = torch.nn.functional.normalize(embedding[0], p=2, dim=1).contiguous()           # :377
+    else:
+        embedding = torch.nn.functional.normalize(embedding[0].T, p=2, dim=1)                      # :380
     _, bw, cluster_ids = guard_mean_shift(MeanShift(), embedding, quantile, iterations)            # :382-384
     weights = to_one_hot(cluster_ids, np.unique(cluster_ids.data.cpu().numpy()).shape[0])          # :385-386
     cluster_ids = cluster_ids.data.cpu().numpy()

@@ -108,3 +108,22 @@ def test_driver_flow_end_to_end(dev):
     assert abs(out["s_iou"] - o[0]) < 1e-12 and abs(out["s_recall"] - o[4]) < 1e-12
     params, status, seg_type = drv.stage2_fits(pts, nrm, lab, typ)
     assert (status[: int(lab.max()) + 1] == 0).all()
+    # the same flow with HPNet_embed = True on given spectral vectors: 148-column embedding -> compute_entropy weights ->
+    # tensor-core mean-shift at 192 columns, against the oracle chain
+    import oracle_hpnet as OH
+    g = torch.Generator().manual_seed(3)
+    v = torch.randn((1, n, 12), generator=g)
+    v = v / (torch.norm(v, dim=-1, keepdim=True) + 1e-16)
+    out_h = drv.predict_shape(drv.build_model(sd_t, k), drv.build_model(sd_i, k), t(pts)[None], t(nrm)[None], lab[None], typ[None],
+                              spectral_v=v, spectral_ent=torch.tensor(0.3), chunk=400)
+    with torch.no_grad():
+        sdt, sdi = {kk: t(vv) for kk, vv in sd_t.items()}, {kk: t(vv) for kk, vv in sd_i.items()}
+        x6 = torch.cat([t(pts)[None], t(nrm)[None]], 2).permute(0, 2, 1)
+        logp = O.sednet_forward(sdt, x6, k)[1]
+        fo = O.sednet_forward(sdi, x6, k)
+        emb = OH.hpnet_combine(fo[0].transpose(1, 2), v, torch.tensor(0.3), logp.transpose(1, 2), fo[3].transpose(1, 2), 0.5, 400)
+        X = torch.nn.functional.normalize(emb[0], p=2, dim=1)
+        _, rbw, rlab = O.guard_mean_shift(X, 0.015, 50)
+    assert X.shape[1] == 148 and (canon(out_h["cluster_ids"]) == canon(rlab.numpy())).all()
+    assert abs(out_h["bw"] - float(rbw)) < 1e-3 * float(rbw)
+
