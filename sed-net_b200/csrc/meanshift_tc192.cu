@@ -2,19 +2,18 @@
 // reference src/smooth_normal_matrix.py:221-233 -> src/mean_shift.py:45-79).  Same scheme as meanshift_tc.cu --
 // flash-style pass, FP16 hi/lo split operands, S = Qh Xh + Qh Xl + Ql Xh (FP32-faithful), P = K(S) in FP16 written over
 // S in TMEM, O += Ph Xh -- re-laid-out for 192-wide rows:
-//   TMEM   S [0,128)   O [128,320)   Q_hi [320,416)   Q_lo [416,512)          (all 512 columns)
-//   smem   2 stages x [X_hi: 3 boxes of 64 channels | X_lo: 3 boxes] = 2 x 96 KB
-// O needs 192 accumulator columns and Q 2 x 96, which leaves ONE S buffer: the S MMAs of tile j+1 cannot overlap the exp
-// work of tile j as they do in the 128-wide kernel (the tensor pipe waits ~20 % of the time), but the iteration still
-// runs ~25x faster than the FP32 FFMA kernel.  Both exp groups work on the same tile (two 32-key chunks each); because P
-// (16 columns per chunk) lands on columns another group may still have to read as S, every thread first loads its S
-// chunks, then all eight warps meet at a named barrier, then P is stored.
+//   TMEM   S0 [0,64)  S1 [64,128)   O [128,320)   Q_hi [320,416)   Q_lo [416,512)          (all 512 columns)
+//   smem   4 stages x [X_hi: 3 boxes of 64 keys x 64 channels | X_lo: 3 boxes] = 4 x 48 KB
+// O needs 192 accumulator columns and Q 2 x 96, which leaves 128 columns for S: the key tile is 64 wide (not 128) so that
+// S stays double-buffered -- the S MMAs of tile j+1 overlap the exp work of tile j, exp group g serving the tiles of
+// buffer g, exactly as in the 128-wide kernel.
 #include "tc_common.cuh"
 
 namespace sed {
 
-constexpr int W_M = 128, W_NK = 128, W_D = 192, W_THREADS = 320, W_STAGES = 2;
-constexpr uint32_t W_PART = 3 * BOX_BYTES;            // one operand part (hi or lo) of a 128 x 192 tile: 48 KB
+constexpr int W_M = 128, W_NK = 64, W_D = 192, W_THREADS = 320, W_STAGES = 4;
+constexpr uint32_t W_XBOX = W_NK * 128;               // one TMA box of the key tile: 64 keys x 64 channels fp16 = 8 KB
+constexpr uint32_t W_PART = 3 * W_XBOX;               // one operand part (hi or lo) of a 64 x 192 tile: 24 KB
 constexpr uint32_t W_STAGE = 2 * W_PART;
 constexpr uint32_t W_COL_O = 128, W_COL_QH = 320, W_COL_QL = 416;
 constexpr float kWScale = 8.0f;
@@ -37,9 +36,9 @@ ms_shift_tc192_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     const uint32_t bar_q_full = bar_base;
     const uint32_t bar_x_full = bar_base + 8;                    // [W_STAGES]
     const uint32_t bar_x_empty = bar_x_full + 8 * W_STAGES;      // [W_STAGES]
-    const uint32_t bar_s_full = bar_x_empty + 8 * W_STAGES;
-    const uint32_t bar_p_full = bar_s_full + 8;
-    const uint32_t bar_o_full = bar_p_full + 8;
+    const uint32_t bar_s_full = bar_x_empty + 8 * W_STAGES;      // [2]
+    const uint32_t bar_p_full = bar_s_full + 16;                 // [2]
+    const uint32_t bar_o_full = bar_p_full + 16;
     const uint32_t tmem_slot = bar_o_full + 8;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -51,8 +50,7 @@ ms_shift_tc192_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
     if (threadIdx.x == 0) {
         mbar_init(bar_q_full, 256);
         for (int s = 0; s < W_STAGES; ++s) { mbar_init(bar_x_full + 8 * s, 1); mbar_init(bar_x_empty + 8 * s, 1); }
-        mbar_init(bar_s_full, 1);
-        mbar_init(bar_p_full, 256);
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_s_full + 8 * i, 1); mbar_init(bar_p_full + 8 * i, 128); }
         mbar_init(bar_o_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -75,8 +73,8 @@ ms_shift_tc192_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                 mbar_expect_tx(bar, W_STAGE);
 #pragma unroll
                 for (int box = 0; box < 3; ++box) {
-                    tma_load_3d(dst + box * BOX_BYTES, &map_xh, bar, box * 64, j * W_NK, b);
-                    tma_load_3d(dst + W_PART + box * BOX_BYTES, &map_xl, bar, box * 64, j * W_NK, b);
+                    tma_load_3d(dst + box * W_XBOX, &map_xh, bar, box * 64, j * W_NK, b);
+                    tma_load_3d(dst + W_PART + box * W_XBOX, &map_xl, bar, box * 64, j * W_NK, b);
                 }
             }
         }
@@ -84,14 +82,10 @@ ms_shift_tc192_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
         // ============================================================ MMA issuer (one elected thread)
         if (elect_one()) {
             constexpr uint32_t IDESC_S = make_idesc_n(0, W_NK), IDESC_PV = make_idesc_n(1, W_D);
-            mbar_wait(bar_q_full, 0);
-            for (int j = 0; j < T; ++j) {
-                const int s = j % W_STAGES;
-                const uint32_t xs = x_addr + s * W_STAGE;
-                mbar_wait(bar_x_full + 8 * s, (j / W_STAGES) & 1);
-                tc_fence_after();
-                // S(j) = Qh Xh + Qh Xl + Ql Xh over 192 channels = 12 K-steps of 16 (tcgen05 MMAs of one thread execute in
-                // issue order: S(j) overwrites the buffer only after PV(j-1) has read P(j-1) from it)
+            // S(j) = Qh Xh + Qh Xl + Ql Xh over 192 channels = 12 K-steps of 16, into S buffer j & 1
+            auto issue_s = [&](int j) {
+                const uint32_t xs = x_addr + (j % W_STAGES) * W_STAGE;
+                const uint32_t d = tmem + (uint32_t)(j & 1) * 64u;
                 uint32_t acc = 0;
 #pragma unroll
                 for (int term = 0; term < 3; ++term) {
@@ -99,20 +93,33 @@ ms_shift_tc192_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                     const uint32_t xb = xs + (term == 1 ? W_PART : 0);
 #pragma unroll
                     for (int ks = 0; ks < W_D / 16; ++ks) {
-                        const uint32_t off = (ks >> 2) * BOX_BYTES + (ks & 3) * 32;
-                        umma_ts(tmem, qa + ks * 8, make_desc(xb + off, 16), IDESC_S, acc);
+                        const uint32_t off = (ks >> 2) * W_XBOX + (ks & 3) * 32;
+                        umma_ts(d, qa + ks * 8, make_desc(xb + off, 16), IDESC_S, acc);
                         acc = 1;
                     }
                 }
-                tc_commit(bar_s_full);
-                mbar_wait(bar_p_full, j & 1);
+            };
+            mbar_wait(bar_q_full, 0);
+            mbar_wait(bar_x_full, 0);
+            tc_fence_after();
+            issue_s(0);
+            tc_commit(bar_s_full);
+            for (int j = 0; j < T; ++j) {
+                if (j + 1 < T) {
+                    mbar_wait(bar_x_full + 8 * ((j + 1) % W_STAGES), ((j + 1) / W_STAGES) & 1);
+                    tc_fence_after();
+                    issue_s(j + 1);
+                    tc_commit(bar_s_full + 8 * ((j + 1) & 1));
+                }
+                mbar_wait(bar_p_full + 8 * (j & 1), (j >> 1) & 1);
                 tc_fence_after();
                 // O += P(j) Xh(j): A = P in TMEM (8 columns per K-step of 16 keys), B = the X_hi tile MN-major, N = 192
+                const uint32_t xs = x_addr + (j % W_STAGES) * W_STAGE;
+                const uint32_t pa = tmem + (uint32_t)(j & 1) * 64u;
 #pragma unroll
                 for (int ks = 0; ks < W_NK / 16; ++ks)
-                    umma_ts(tmem + W_COL_O, tmem + ks * 8, make_desc(xs + ks * 2048, BOX_BYTES), IDESC_PV,
-                            (j > 0 || ks > 0) ? 1u : 0u);
-                tc_commit(bar_x_empty + 8 * s);
+                    umma_ts(tmem + W_COL_O, pa + ks * 8, make_desc(xs + ks * 2048, W_XBOX), IDESC_PV, (j > 0 || ks > 0) ? 1u : 0u);
+                tc_commit(bar_x_empty + 8 * (j % W_STAGES));
             }
             tc_commit(bar_o_full);
         }
@@ -146,22 +153,19 @@ ms_shift_tc192_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             tc_fence_before();
             mbar_arrive(bar_q_full);
         }
-        const uint32_t sb = tmem + lane_addr;
-        for (int j = 0; j < T; ++j) {
-            mbar_wait(bar_s_full, j & 1);
+        for (int j = group; j < T; j += 2) {
+            const uint32_t sb = tmem + lane_addr + (uint32_t)(j & 1) * 64u;
+            mbar_wait(bar_s_full + 8 * (j & 1), (j >> 1) & 1);
             tc_fence_after();
-            uint32_t v0[32], v1[32];
-            tmem_ld32(sb + (group * 2) * 32, v0);
-            tmem_ld32(sb + (group * 2 + 1) * 32, v1);
-            tmem_ld_wait();
-            asm volatile("bar.sync 1, 256;" ::: "memory");        // every S chunk is in registers: P may overwrite S
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(sb + c * 32, v);
+                tmem_ld_wait();
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float s0 = __uint_as_float(cc == 0 ? v0[2 * i] : v1[2 * i]);
-                    const float s1 = __uint_as_float(cc == 0 ? v0[2 * i + 1] : v1[2 * i + 1]);
+                    const float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
                     float p0, p1;
                     if (KT == 0) {
                         p0 = ex2_approx(fmaf(s0, c1, c0));
@@ -173,11 +177,11 @@ ms_shift_tc192_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
                     const __half2 h = __floats2half2_rn(p0, p1);
                     pk[i] = *reinterpret_cast<const uint32_t*>(&h);
                 }
-                tmem_st16(sb + (group * 2 + cc) * 16, pk);
+                tmem_st16(sb + c * 16, pk);   // P (fp16) overwrites the S columns this thread has already consumed
             }
             tmem_st_wait();
             tc_fence_before();
-            mbar_arrive(bar_p_full);
+            mbar_arrive(bar_p_full + 8 * (j & 1));
         }
         // ---- epilogue: new = O / ||O||.  Thread (row, group) owns three of the row's six 32-channel chunks.
         mbar_wait(bar_o_full, 0);
@@ -273,8 +277,8 @@ int ms_shift_tc192(const float* X, const float* bw, int B, int N, int d, int ite
     split192_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, st>>>(X, (long long)elems, d, xh, xl);
     ++g_sed_launches;
     CUtensorMap mxh, mxl;
-    int rc = make_map_f16(&mxh, xh, B, N, W_D);
-    if (rc == SED_OK) rc = make_map_f16(&mxl, xl, B, N, W_D);
+    int rc = make_map_f16(&mxh, xh, B, N, W_D, W_NK);
+    if (rc == SED_OK) rc = make_map_f16(&mxl, xl, B, N, W_D, W_NK);
     constexpr size_t smem = (size_t)W_STAGES * W_STAGE + 1024 + 256;
     const int qtc = (N + W_M - 1) / W_M;
     if (rc == SED_OK) {
