@@ -11,10 +11,11 @@ does.
 Parity pin: the reference ships no golden vectors or asserting tests for this
 path, so this restatement is pinned against the
 UNMODIFIED reference executed in the build container (``oracle/ref_shim.py``):
-``oracle/check_oracle.py`` compares every function below with the real
-reference on seeded inputs, and ``oracle/make_golden.py`` writes the
-reference's outputs to ``tests/golden/*.npz`` which the CPU test-suite replays
-against this file (tests/test_oracle_golden.py).
+``oracle/make_golden.py`` / ``oracle/make_golden_dispatch.py`` compare every
+function below with the real reference on seeded inputs (the diffs they print
+are 0 or rounding-order noise) and write the reference's outputs to
+``tests/golden/*.npz``, which the CPU test-suite replays against this file
+(tests/test_oracle_golden.py).
 """
 import math
 
@@ -409,6 +410,65 @@ def fit_segments(points, normals, labels, seg_type, min_pts=20):
             res[s] = ("sphere",) + tuple(fit_sphere(p, n, w))
     return res
 
+
+
+def fit_one_shape(data, weights, eval=True):
+    """src/primitive_forward.py:929-1051 (fit_one_shape_torch) restricted to the analytic
+    types, with the FittingModule.forward_pass_{plane,cone,cylinder,sphere} bookkeeping of
+    src/fitting_optimization.py:160-245 inlined: returns ``parameters`` exactly as
+    ``fitter.fitting.parameters`` is left by the reference --
+        ids -> ["plane", axis (3,1), d] | ["cone", apex (1,3), axis (3,1), theta] |
+               ["cylinder", a (3,1), center (1,3), radius] | ["sphere", center (1,3), radius] | None
+    ``data``: list of [points, normals, type id, gpoints, segment_indices, (part_index, label_index)]
+    as built by Evaluation.residual_eval_mode (Fitting_patches_and_edges/residual_utils.py:210-285);
+    ``weights`` (N, C).  Spline types (0, 2, 6, 7, 8, 9) need SplineNet and are outside the
+    path: patches under 100 points are dropped as in the reference (:985-990, :1027-1031),
+    larger ones raise."""
+    parameters = {}
+    for d in data:
+        points, normals, labels, _, segment_indices, (part_index, label_index) = d
+        if not eval:                                                    # :945-963 (training: every 2nd point, twice)
+            weight = weights[:, part_index:part_index + 1] + EPS
+            drop = torch.arange(0, points.shape[0], 2)
+            points, normals, weight = points[drop], normals[drop], weight[drop]
+            if labels not in [0, 2, 6, 7, 9, 8]:
+                drop = torch.arange(0, points.shape[0], 2)
+                points, normals, weight = points[drop], normals[drop], weight[drop]
+        else:
+            weight = weights[segment_indices, part_index:part_index + 1] + EPS   # :954
+        if points.shape[0] < 20:                                        # :974-978
+            parameters[label_index] = None
+            continue
+        if labels in [0, 9, 6, 7, 2, 8]:
+            if points.shape[0] < 100:                                   # :983-990, :1027-1031
+                parameters[label_index] = None
+                continue
+            raise NotImplementedError("spline patches need SplineNet (outside the hot path)")
+        if labels == 1:                                                 # :1004-1007 -> fitting_optimization.py:160-167
+            a, dd = fit_plane(points, normals, weight)
+            parameters[label_index] = ["plane", a.reshape((3, 1)), dd]
+        elif labels == 3:                                               # :1009-1012 -> :184-196
+            apex, axis, theta = fit_cone(points, normals, weight)
+            parameters[label_index] = ["cone", apex.reshape((1, 3)), axis.reshape((3, 1)), theta]
+        elif labels == 4:                                               # :1014-1017 -> :208-215
+            a, center, radius = fit_cylinder(points, normals, weight)
+            parameters[label_index] = ["cylinder", a, center, radius]
+        elif labels == 5:                                               # :1019-1022 -> :230-237
+            center, radius = fit_sphere(points, normals, weight)
+            parameters[label_index] = ["sphere", center, radius]
+    return parameters
+
+
+def residual_loss(Points, parameters, sqrt=False, reduce=True):
+    """src/primitives.py:36-44 over the dict ``fit_one_shape`` returns."""
+    fn = dict(plane=distance_from_plane, sphere=distance_from_sphere, cylinder=distance_from_cylinder,
+              cone=distance_from_cone)
+    out = {}
+    for k, v in parameters.items():
+        if v is None:
+            continue
+        out[k] = [v[0], fn[v[0]](Points[k], *v[1:], sqrt=sqrt, reduce=reduce)]
+    return out
 
 def residuals(points, labels, fits, sqrt=True):
     """src/primitives.py:36-44 (ResidualLoss.residual_loss, reduce=True)."""

@@ -80,7 +80,9 @@ def test_fits_golden(golden):
             c, a, th = O.fit_cone(P, Nn, W)
             got = np.concatenate([c.numpy().ravel(), a.numpy().ravel(), [float(th)]])
             dist = O.distance_from_cone(P, t(ref[:3]), t(ref[3:6]), t(ref[6:7]), sqrt=True, reduce=False)
-        assert rel_err(got, ref) < 2e-3, (key, got, ref)
+        # oracle == unmodified reference bit for bit in the container that recorded the vectors (make_golden.py prints 0);
+        # 1e-5 leaves room for another CPU's BLAS kernels only
+        assert rel_err(got, ref) < 1e-5, (key, got, ref)
         assert np.max(np.abs(dist.numpy() - g[key + "_dist"])) < 1e-5, key
 
 

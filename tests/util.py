@@ -69,3 +69,26 @@ def cylinder_fp64(p, n, w, eps32=float(np.finfo(np.float32).eps)):
     c = -np.linalg.solve(AtA + lam * np.eye(3), A.T @ Y)
     r2 = (w[:, 0] * ((v - c) ** 2).sum(1)).sum() / ws
     return ax, c, float(np.sqrt(max(r2, 1e-3)))
+
+
+def flat_params(v):
+    """["name", tensors...] of fitting.parameters -> flat float64 vector."""
+    return np.concatenate([np.asarray(x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x, np.float64).ravel()
+                           for x in v[1:]])
+
+
+def comparable_params(name, got, ref):
+    """Resolve the conventions the reference leaves open before comparing a fit with a recorded one: the sign of a plane's
+    (a, d) and of a cylinder's axis follow LAPACK's singular vector; a cylinder's centre is only determined orthogonally
+    to its axis (SURVEY.md 7.3-4,5).  Returns (got', ref') flat vectors."""
+    got, ref = np.asarray(got, np.float64).ravel().copy(), np.asarray(ref, np.float64).ravel().copy()
+    if name == "plane":
+        if got[:3] @ ref[:3] < 0:
+            got = -got
+    elif name == "cylinder":
+        if got[:3] @ ref[:3] < 0:
+            got[:3] = -got[:3]
+        ax = ref[:3]
+        got[3:6] -= (got[3:6] @ ax) * ax
+        ref[3:6] -= (ref[3:6] @ ax) * ax
+    return got, ref
