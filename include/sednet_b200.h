@@ -10,7 +10,8 @@
  * Conventions
  *   - plain C types only; all pointers are DEVICE pointers unless the name ends in _host;
  *   - every function returns int: 0 = ok, SED_ERR_ARG (-1) bad argument, SED_ERR_UNSUPPORTED (-2) shape outside
- *     the compiled range, -(1000 + cudaError_t) for CUDA failures; never throws, never exits;
+ *     the compiled range, SED_ERR_GUARD (-3) the guarded mean-shift ran out of quantile (the reference raises there),
+ *     -(1000 + cudaError_t) for CUDA failures; never throws, never exits;
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point synchronises the device
  *     unless documented ("host sync");
  *   - tensors are dense row-major in the stated shape, f32 unless stated; indices/labels are int64 where the
@@ -28,6 +29,7 @@ extern "C" {
 #define SED_OK 0
 #define SED_ERR_ARG (-1)
 #define SED_ERR_UNSUPPORTED (-2)
+#define SED_ERR_GUARD (-3)
 #define SED_ERR_CUDA_BASE (-1000)
 
 typedef void* sed_stream_t; /* cudaStream_t */
@@ -156,11 +158,14 @@ int sed_ms_bandwidth(const float* X, int B, int N, int d, int K, float min_bw, f
                      sed_stream_t stream);
 
 /* src/mean_shift.py:45-79 mean_shift_: `iterations` fixed shifts on the unit hypersphere.
- *   X (B,N,d), d <= 256 a multiple of 4, bw (B) device, kernel_type 0 gaussian / 1 epanechnikov, prec_mode 0 = FP32 FFMA
- *   (reference operation order; the only mode for d > 128, e.g. the 148-column hpnet embedding), tcgen05 modes (d <= 128, zero-padded to 128 columns) with FP16 hi/lo split operands and FP32
- *   accumulation:
- *   1 = S from 3 MMAs (Qh.Xh + Qh.Xl + Ql.Xh), O from 2 (Ph.Xh + Ph.Xl);  3 = S from 3, O from 1 (Ph.Xh);
- *   2 = single FP16 pass for both (fast, not FP32-faithful).
+ *   X (B,N,d), d <= 256 a multiple of 4, bw (B) device, kernel_type 0 gaussian / 1 epanechnikov.
+ *   prec_mode 0 = FP32 FFMA in the reference's operation order (any d <= 256).  Tensor-core modes (tcgen05, FP16 hi/lo
+ *   split operands, FP32 accumulation; rows zero-padded to 128 or 192 columns):
+ *     1 = S from 3 MMAs (Qh.Xh + Qh.Xl + Ql.Xh), O from 2 (Ph.Xh + Ph.Xl): FP32-faithful on both legs (d <= 128;
+ *         for 128 < d <= 256 the call runs mode 0, which is at least as accurate);
+ *     3 = S from 3 MMAs, O from 1 (Ph.Xh): the exponent is FP32-faithful, the weighted mean carries one FP16 rounding of
+ *         X per term (d <= 192; wider rows run mode 0);
+ *     2 = single FP16 pass for both legs (d <= 128; fast, not FP32-faithful); for 128 < d <= 192 it runs as mode 3.
  *   out (B,N,d); tmp (B,N,d) scratch (ping-pong). */
 int sed_ms_shift(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type,
                  int prec_mode, float* out, float* tmp, sed_stream_t stream);

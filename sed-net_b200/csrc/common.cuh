@@ -7,6 +7,7 @@
 #define SED_OK 0
 #define SED_ERR_ARG (-1)
 #define SED_ERR_UNSUPPORTED (-2)
+#define SED_ERR_GUARD (-3)
 #define SED_ERR_CUDA_BASE (-1000)  // -(1000 + cudaError_t)
 
 // counts kernel launches issued by the library (sed_launch_count); atomic: the entry points may be called from

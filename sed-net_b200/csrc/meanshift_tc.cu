@@ -311,7 +311,14 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             }
             ssx[group * 128 + row] = ss;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float rn = 1.0f / sqrtf(ssx[row] + ssx[128 + row]);
+            // A row whose every weight underflows FP16 (all keys farther than ~5.8 b: it cannot happen to a row that
+            // started on a key, whose own weight is 1, but a caller may shift foreign points) has O = 0.  The reference
+            // clamps the exponent at -75 so its sum stays positive; here such a row is left where it is instead of
+            // becoming NaN.  The test is warp-uniform because tcgen05.ld is.
+            const float sst = ssx[row] + ssx[128 + row];
+            const bool dead = !(sst > 0.f);
+            const bool any_dead = __any_sync(0xffffffffu, dead);
+            const float rn = dead ? 1.0f / kOperandScale : 1.0f / sqrtf(sst);
             const int q = q0 + row;
             const long long rowoff = ((long long)b * N + q) * TC_D;
 #pragma unroll
@@ -319,6 +326,23 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 const int c = group * 2 + cc;
                 float z[32];
                 get_chunk(c, z);
+                if (any_dead) {
+                    uint32_t qh16[16], ql16[16];
+                    tmem_ld16(tmem + lane_addr + 384u + (uint32_t)c * 16u, qh16);
+                    if (HAS_LO) tmem_ld16(tmem + lane_addr + 448u + (uint32_t)c * 16u, ql16);
+                    tmem_ld_wait();
+                    if (dead) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            float2 v = __half22float2(*reinterpret_cast<const __half2*>(&qh16[i]));
+                            if (HAS_LO) {
+                                const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&ql16[i]));
+                                v.x += l.x; v.y += l.y;
+                            }
+                            z[2 * i] = v.x; z[2 * i + 1] = v.y;
+                        }
+                    }
+                }
                 if (q < N) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) z[i] *= rn;
@@ -401,7 +425,12 @@ int ms_shift_tc192(const float* X, const float* bw, int B, int N, int d, int ite
 int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type, int prec_mode,
                 float* out, float* tmp, cudaStream_t st) {
     (void)tmp;
-    if (d > TC_D) return ms_shift_tc192(X, bw, B, N, d, iterations, kernel_type, out, st);   // 129..192 columns
+    if (d > TC_D) {
+        // 129..192 columns: the only tensor-core kernel at that width runs the 3 + 1 split.  Mode 1 asks for both legs at
+        // FP32 accuracy: send it to the caller's FP32 FFMA kernel rather than silently running 3 + 1.
+        if (prec_mode == 1) return SED_ERR_UNSUPPORTED;
+        return ms_shift_tc192(X, bw, B, N, d, iterations, kernel_type, out, st);
+    }
     if (d <= 0 || (d & 3)) return SED_ERR_UNSUPPORTED;
     const bool padded = d < TC_D;      // the kernel works on 128-wide rows: pad with zero columns, strip them at the end
     const bool has_lo = (prec_mode == 1 || prec_mode == 3);

@@ -199,7 +199,11 @@ ms_shift_tc192_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
         }
         ssx[group * 128 + row] = ss;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float rn = 1.0f / sqrtf(ssx[row] + ssx[128 + row]);
+        // a row whose every weight underflows FP16 keeps its position instead of becoming NaN (see meanshift_tc.cu)
+        const float sst = ssx[row] + ssx[128 + row];
+        const bool dead = !(sst > 0.f);
+        const bool any_dead = __any_sync(0xffffffffu, dead);
+        const float rn = dead ? 1.0f / kWScale : 1.0f / sqrtf(sst);
         const int q = q0 + row;
         const long long rowoff = ((long long)b * N + q) * W_D;
 #pragma unroll
@@ -208,6 +212,21 @@ ms_shift_tc192_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_c
             uint32_t v[32];
             tmem_ld32(ob + c * 32, v);
             tmem_ld_wait();
+            if (any_dead) {
+                uint32_t qh16[16], ql16[16];
+                tmem_ld16(tmem + lane_addr + W_COL_QH + (uint32_t)c * 16u, qh16);
+                tmem_ld16(tmem + lane_addr + W_COL_QL + (uint32_t)c * 16u, ql16);
+                tmem_ld_wait();
+                if (dead) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&qh16[i]));
+                        const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&ql16[i]));
+                        v[2 * i] = __float_as_uint(h.x + l.x);
+                        v[2 * i + 1] = __float_as_uint(h.y + l.y);
+                    }
+                }
+            }
             if (q < N) {
                 float z[32];
 #pragma unroll

@@ -95,6 +95,7 @@ const char* sed_error_string(int code) {
     if (code == SED_OK) return "ok";
     if (code == SED_ERR_ARG) return "invalid argument";
     if (code == SED_ERR_UNSUPPORTED) return "shape outside the compiled range";
+    if (code == SED_ERR_GUARD) return "guarded mean-shift did not reach <= 49 clusters before K = int(quantile * 10000) exceeded N";
     if (code <= SED_ERR_CUDA_BASE) return cudaGetErrorString((cudaError_t)(-(code - SED_ERR_CUDA_BASE)));
     return "unknown error";
 }
@@ -122,6 +123,10 @@ void sed_pipeline_destroy(sed_pipeline_t* p) {
 
 int sed_pipeline_create(int max_B, int N, int k, int max_segments, sed_pipeline_t** out) {
     if (!out || max_B <= 0 || N <= 0 || k <= 0 || k > N || max_segments <= 0 || max_segments > 512) return SED_ERR_ARG;
+    // The driver calls mean_shift(X, 10000, q, ...): compute_bandwidth takes K = int(q * 10000) whatever N is, over all N
+    // rows only while N <= 10000 (src/mean_shift.py:122-129 subsamples 10 000 rows with NumPy's RNG above that); the
+    // handle runs the all-rows form, so larger clouds are refused instead of silently getting a smaller bandwidth.
+    if (N > 10000) return SED_ERR_UNSUPPORTED;
     sed_pipeline* p = new (std::nothrow) sed_pipeline();
     if (!p) return SED_ERR_ARG;
     memset(p, 0, sizeof(*p));
@@ -235,13 +240,16 @@ int sed_pipeline_run_cluster(sed_pipeline_t* p, const float* points_dev, const f
     SED_CUDA(cudaMemcpyAsync(p->h_counts, p->n_labels, B * sizeof(int), cudaMemcpyDeviceToHost, st));
     SED_CUDA(cudaMemcpyAsync(p->h_counts + p->max_B, p->n_centers, B * sizeof(int), cudaMemcpyDeviceToHost, st));
     SED_CUDA(cudaStreamSynchronize(st));
+    // The reference's loop is `while True: ...; if unique(labels) > 49: quantile *= 1.2 else break`
+    // (generate_predictions_aug.py:25-35); it ends by raising from topk once K = int(quantile * 10000) exceeds N.  Same
+    // here: K runs 150, 180, 216, 259, ... up to N (the K-th select has 16-bit counters for K > 255), and a cloud that
+    // still has > 49 labels (or more centres than the handle's max_segments) when K would pass N fails the call with
+    // SED_ERR_GUARD -- never SED_OK with labels that the type vote / fits cannot index.
     for (int b = 0; b < B; ++b) {
         double q = quantile;
-        int tries = 0;
-        while ((p->h_counts[b] > 49 || p->h_counts[p->max_B + b] < 0) && tries < 64) {
+        while (p->h_counts[b] > 49 || p->h_counts[p->max_B + b] < 0) {
             q *= 1.2;
-            ++tries;
-            if ((int)(q * 10000.0) > N) break;  // the reference's topk would raise here
+            if ((int)(q * 10000.0) > N) return SED_ERR_GUARD;
             ++p->retries;
             SED_TRY(pipe_mean_shift(p, b, 1, q, iterations, prec_mode, false, st));
             SED_CUDA(cudaMemcpyAsync(p->h_counts + b, p->n_labels + b, sizeof(int), cudaMemcpyDeviceToHost, st));

@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "tc_common.cuh"
 
 namespace sed {
@@ -75,18 +77,25 @@ __device__ __forceinline__ float sel_score(float acc0, float acc1, float inv_s2,
     }
 }
 
-// KB: 64-channel boxes per operand row (1: K <= 64, 2: K = 128).  RBITS: radix bits per pass.
-template <int MODE, int OUT, int KB, int RBITS>
+// KB: 64-channel boxes per operand row (1: K <= 64, 2: K = 128).  RBITS: radix bits per pass.  CB: bytes per histogram
+// counter -- 1 (saturating at 255: ranks k <= 255) or 2 (ranks up to 65 535: the K-th-neighbour select of a guard retry
+// with a large quantile, src/mean_shift.py:81-96; one candidate stage less to make room for the wider histograms).
+template <int KB, int CB>
+struct SelStages { static constexpr int value = (CB == 2) ? (KB == 1 ? 3 : 1) : ((KB == 1) ? 3 : (KB == 2 ? 2 : 1)); };
+
+template <int MODE, int OUT, int KB, int RBITS, int CB = 1>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_constant__ CUtensorMap map_ql,
                  const __grid_constant__ CUtensorMap map_xh, const __grid_constant__ CUtensorMap map_xl, SelParams p) {
     constexpr uint32_t PART_BYTES = KB * BOX_BYTES;
     constexpr uint32_t TILE2 = 2 * PART_BYTES;                     // hi + lo
-    constexpr int STAGES = (KB == 1) ? 3 : (KB == 2 ? 2 : 1);   // KB = 3 (192-wide rows): one 96 KB candidate stage
+    constexpr int STAGES = SelStages<KB, CB>::value;             // KB = 3 (192-wide rows): one 96 KB candidate stage
+    typedef typename std::conditional<CB == 1, uint8_t, uint16_t>::type CT;
+    constexpr uint32_t CMAX = (CB == 1) ? 255u : 65535u;
     constexpr int NBINS = 1 << RBITS;
     constexpr int NPASS_RADIX = (OUT == OUT_TOP1) ? 0 : (32 + RBITS - 1) / RBITS;
     constexpr int NPASS = (OUT == OUT_TOP1) ? 1 : NPASS_RADIX + (OUT == OUT_IDX ? 1 : 0);
-    constexpr uint32_t HIST_BYTES = NBINS * 128;                    // one group's u8 histogram
+    constexpr uint32_t HIST_BYTES = NBINS * 128 * CB;               // one group's histogram
     constexpr uint32_t SEL_BYTES = (OUT == OUT_TOP1) ? 1024 : 2 * HIST_BYTES;   // lists (48 KB) alias the histograms
     static_assert(OUT != OUT_IDX || 2 * HIST_BYTES >= ST_KMAX * 128 * 6, "lists must fit in the histogram area");
     constexpr int NACC = 2;   // PN: points / normals Grams; L2, COS: hi.hi and the cross terms (summed in FP32 RN by the
@@ -207,9 +216,9 @@ select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_consta
         const float xq = (MODE == SEL_COS) ? 0.f : p.xxq[(long long)b * p.npad + min(q, p.npad - 1)];
         const float* xxc = (MODE == SEL_COS) ? nullptr : p.xxc + (long long)b * p.npad;
         // u8 saturating counters hist[g][bin][slot], slot = lane*4 + quarter: every lane of a warp on its own bank.
-        // Saturation at 255 is exact enough: bins ABOVE the one holding rank k_rem (<= 255) hold fewer than k_rem.
-        uint8_t* hist = sel_ptr + group * HIST_BYTES + lane * 4 + quarter;
-        const uint8_t* hist_o = sel_ptr + (group ^ 1) * HIST_BYTES + lane * 4 + quarter;
+        // Saturation at CMAX is exact: bins ABOVE the one holding rank k_rem (<= CMAX) hold fewer than k_rem.
+        CT* hist = reinterpret_cast<CT*>(sel_ptr + group * HIST_BYTES) + lane * 4 + quarter;
+        const CT* hist_o = reinterpret_cast<const CT*>(sel_ptr + (group ^ 1) * HIST_BYTES) + lane * 4 + quarter;
         uint32_t* lkey = reinterpret_cast<uint32_t*>(sel_ptr) + row;                                   // lkey[pos * 128]
         uint16_t* lidx = reinterpret_cast<uint16_t*>(sel_ptr + ST_KMAX * 128 * 4) + row;               // lidx[pos * 128]
 
@@ -277,17 +286,17 @@ select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_consta
                                 m[e] = ((i < nv) && (known == 0 || (key >> (32 - known)) == pref)) ? 1u : 0u;
                                 cn[e] = hist[bn[e] * 128];
                             }
-                            const uint32_t n0 = min(cn[0] + m[0], 255u);
+                            const uint32_t n0 = min(cn[0] + m[0], CMAX);
                             cn[1] = (bn[1] == bn[0]) ? n0 : cn[1];
-                            const uint32_t n1 = min(cn[1] + m[1], 255u);
+                            const uint32_t n1 = min(cn[1] + m[1], CMAX);
                             cn[2] = (bn[2] == bn[1]) ? n1 : ((bn[2] == bn[0]) ? n0 : cn[2]);
-                            const uint32_t n2 = min(cn[2] + m[2], 255u);
+                            const uint32_t n2 = min(cn[2] + m[2], CMAX);
                             cn[3] = (bn[3] == bn[2]) ? n2 : ((bn[3] == bn[1]) ? n1 : ((bn[3] == bn[0]) ? n0 : cn[3]));
-                            const uint32_t n3 = min(cn[3] + m[3], 255u);
-                            hist[bn[0] * 128] = (uint8_t)n0;
-                            hist[bn[1] * 128] = (uint8_t)n1;
-                            hist[bn[2] * 128] = (uint8_t)n2;
-                            hist[bn[3] * 128] = (uint8_t)n3;
+                            const uint32_t n3 = min(cn[3] + m[3], CMAX);
+                            hist[bn[0] * 128] = (CT)n0;
+                            hist[bn[1] * 128] = (CT)n1;
+                            hist[bn[2] * 128] = (CT)n2;
+                            hist[bn[3] * 128] = (CT)n3;
                         }
                     } else if (radix) {
                         // sparse passes: few candidates still match the prefix
@@ -296,7 +305,7 @@ select_tc_kernel(const __grid_constant__ CUtensorMap map_qh, const __grid_consta
                             const uint32_t key = v0[i];
                             if ((i < nv) && (key >> (32 - known)) == pref) {
                                 const uint32_t bin = (key >> shift) & bmask;
-                                hist[bin * 128] = (uint8_t)min((uint32_t)hist[bin * 128] + 1u, 255u);
+                                hist[bin * 128] = (CT)min((uint32_t)hist[bin * 128] + 1u, CMAX);
                             }
                         }
                     } else {
@@ -1167,15 +1176,15 @@ __global__ void pack_rm_kernel(const float* __restrict__ x, long long rows, int 
     }
 }
 
-template <int MODE, int OUT, int KB, int RBITS>
+template <int MODE, int OUT, int KB, int RBITS, int CB = 1>
 static int launch_select(const CUtensorMap& qh, const CUtensorMap& ql, const CUtensorMap& xh, const CUtensorMap& xl,
                          const SelParams& p, int B, cudaStream_t st) {
-    constexpr int STAGES = (KB == 1) ? 3 : (KB == 2 ? 2 : 1);   // KB = 3 (192-wide rows): one 96 KB candidate stage
+    constexpr int STAGES = SelStages<KB, CB>::value;
     constexpr int NBINS = 1 << RBITS;
-    constexpr size_t SEL = (OUT == OUT_TOP1) ? 1024 : (size_t)2 * NBINS * 128;
+    constexpr size_t SEL = (OUT == OUT_TOP1) ? 1024 : (size_t)2 * NBINS * 128 * CB;
     constexpr size_t smem = (size_t)(STAGES + 1) * 2 * KB * BOX_BYTES + SEL + 1024 + 256;
     static_assert(smem <= 227 * 1024, "shared memory budget");
-    auto kern = select_tc_kernel<MODE, OUT, KB, RBITS>;
+    auto kern = select_tc_kernel<MODE, OUT, KB, RBITS, CB>;
     SED_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((p.Nq + ST_M - 1) / ST_M, B);
     kern<<<grid, ST_THREADS, smem, st>>>(qh, ql, xh, xl, p);
@@ -1231,7 +1240,7 @@ int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn
 //   idx_out != null : index of the best candidate of every row (first on ties)       -> nms membership / labels
 int cos_select_tc(const float* Q, const float* Cand, int B, int Nq, int Nc, const int* nc_ptr, int d, int K,
                   float* kth_out, void* idx_out, int idx64, cudaStream_t st) {
-    if (d > 192 || (d & 3) || Nc >= 65536 || (kth_out && (K > Nc || K <= 0 || K > 255))) return SED_ERR_UNSUPPORTED;
+    if (d > 192 || (d & 3) || Nc >= 65536 || (kth_out && (K > Nc || K <= 0))) return SED_ERR_UNSUPPORTED;
     const int W = d <= 128 ? 128 : 192;   // operand row width: two or three 64-channel boxes
     const bool same = (Q == Cand && Nq == Nc);
     const size_t rq = (size_t)B * Nq, rc_ = (size_t)B * Nc;
@@ -1258,16 +1267,18 @@ int cos_select_tc(const float* Q, const float* Cand, int B, int Nq, int Nc, cons
                 min(max(ks_win, 0), max(KS_CAP - 32 - K - 8, 0)), ks_soft > 0 ? min(max(ks_soft, K + 16), KS_CAP - 33) : 0};
     static const bool radix = [] { const char* e = getenv("SEDNET_B200_KNN"); return e && !strcmp(e, "radix"); }();
     if (rc == SED_OK && W == 192) {   // 129..192 columns (the hpnet embedding): the multi-pass radix kernel, three boxes per row
-        rc = kth_out ? launch_select<SEL_COS, OUT_KTH, 3, 7>(mqh, mql, mch, mcl, p, B, st)
-                     : launch_select<SEL_COS, OUT_TOP1, 3, 8>(mqh, mql, mch, mcl, p, B, st);
+        rc = !kth_out  ? launch_select<SEL_COS, OUT_TOP1, 3, 8>(mqh, mql, mch, mcl, p, B, st)
+             : K <= 255 ? launch_select<SEL_COS, OUT_KTH, 3, 7>(mqh, mql, mch, mcl, p, B, st)
+                        : launch_select<SEL_COS, OUT_KTH, 3, 6, 2>(mqh, mql, mch, mcl, p, B, st);   // 16-bit counters
     } else if (rc == SED_OK && kth_out && K <= KS_KMAX && !radix) {
         CUtensorMap xh64, xl64;   // 64-row candidate tiles
         rc = make_map_f16(&xh64, ch, B, Nc, 128, SS_NC);
         if (rc == SED_OK) rc = make_map_f16(&xl64, cl, B, Nc, 128, SS_NC);
         if (rc == SED_OK) rc = launch_kth_stream(xh64, xl64, qh, ql, p, B, st);
     } else if (rc == SED_OK) {
-        rc = kth_out ? launch_select<SEL_COS, OUT_KTH, 2, 7>(mqh, mql, mch, mcl, p, B, st)
-                     : launch_select<SEL_COS, OUT_TOP1, 2, 8>(mqh, mql, mch, mcl, p, B, st);
+        rc = !kth_out  ? launch_select<SEL_COS, OUT_TOP1, 2, 8>(mqh, mql, mch, mcl, p, B, st)
+             : K <= 255 ? launch_select<SEL_COS, OUT_KTH, 2, 7>(mqh, mql, mch, mcl, p, B, st)
+                        : launch_select<SEL_COS, OUT_KTH, 2, 7, 2>(mqh, mql, mch, mcl, p, B, st);   // 16-bit counters
     }
     cudaFreeAsync(buf, st);
     return rc;

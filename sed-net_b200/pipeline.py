@@ -56,7 +56,7 @@ class Pipeline:
         i, k2 = _host_table(sd_inst)
         _lib.call("sed_pipeline_set_weights", self._h, t, i)
 
-    def run_host(self, points, normals, quantile=0.015, iterations=50, prec_mode=0):
+    def run_host(self, points, normals, quantile=0.015, iterations=50, prec_mode=1):
         """points, normals: (B,N,3) float32 HOST tensors (pinned for full copy speed). Returns dict of host tensors
         (views into pinned result buffers, valid until the next call)."""
         B = points.shape[0]
@@ -70,7 +70,7 @@ class Pipeline:
                   _lib.ptr(o["bw"]), _lib.ptr(o["n_labels"]), _lib.stream())
         return {k: v[:B] for k, v in o.items()}
 
-    def run_device(self, points, normals, quantile=0.015, iterations=50, prec_mode=0):
+    def run_device(self, points, normals, quantile=0.015, iterations=50, prec_mode=1):
         """points, normals: (B,N,3) float32 CUDA tensors; results stay on the device (see ``device_tensor``)."""
         points = _lib.require_cuda(points, name="points")
         normals = _lib.require_cuda(normals, name="normals")
@@ -88,7 +88,7 @@ class Pipeline:
         assert points.shape == (B, self.N, 3) and B <= self.B
         _lib.call("sed_pipeline_run_forward", self._h, _lib.ptr(points), _lib.ptr(normals), B, _lib.stream())
 
-    def run_cluster(self, points, normals, quantile=0.015, iterations=50, prec_mode=0):
+    def run_cluster(self, points, normals, quantile=0.015, iterations=50, prec_mode=1):
         """Second half: guarded mean-shift of the handle's X, type vote, fits, residuals (results on the device)."""
         points = _lib.require_cuda(points, name="points")
         normals = _lib.require_cuda(normals, name="normals")

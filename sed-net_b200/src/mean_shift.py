@@ -11,9 +11,12 @@ MAX_CENTERS = 512
 
 class MeanShift:
     def __init__(self, prec_mode=None):
-        """prec_mode of sed_ms_shift (include/sednet_b200.h): 0 FP32 FFMA, 1 / 3 tcgen05 FP16 hi/lo split (3+2 / 3+1 MMAs),
-        2 plain FP16; None = $SEDNET_B200_MS_PREC if set, otherwise automatic: the FP32-faithful tensor-core mode 3
-        (embeddings up to 192 wide, zero-padded to 128 or 192; identical labels, <= 4e-6 from mode 0), else the FFMA kernel."""
+        """prec_mode of sed_ms_shift (include/sednet_b200.h): 0 FP32 FFMA (reference operation order), 1 tcgen05 with FP16
+        hi/lo split operands on both legs (3 + 2 MMAs: FP32-faithful), 3 the same exponent but a single FP16 pass for the
+        weighted mean (3 + 1 MMAs: faster; one FP16 rounding of X per term), 2 plain FP16.
+        None = $SEDNET_B200_MS_PREC if set, otherwise the FP32-faithful choice for the row width: mode 1 up to 128
+        columns; mode 3 for 129..192 columns (the only tensor-core kernel at that width: the 148-column hpnet embedding,
+        parity-tested against the oracle in tests/test_gpu_hpnet.py); mode 0 beyond.  Mode 3 is opt-in for 128 columns."""
         import os
         env = os.environ.get("SEDNET_B200_MS_PREC")
         self.prec_mode = prec_mode if prec_mode is not None else (int(env) if env is not None else None)
@@ -21,7 +24,9 @@ class MeanShift:
     def _mode(self, d):
         if self.prec_mode is not None:
             return self.prec_mode
-        return 3 if d <= 192 and d % 4 == 0 else 0
+        if d % 4 == 0 and d <= 128:
+            return 1
+        return 3 if d % 4 == 0 and d <= 192 else 0
 
     # -- src/mean_shift.py:19-43
     def mean_shift(self, X, num_samples, quantile, iterations, kernel_type="gaussian", bw=None, nms=True):
@@ -60,20 +65,24 @@ class MeanShift:
                 break
         return center, bandwidth, cluster_ids
 
-    # -- src/mean_shift.py:98-113
+    # -- src/mean_shift.py:98-113 (the N x N kernel matrix itself; mean_shift_ never forms it here, so this is API
+    #    parity for callers that want the matrix: plain tensor ops on X's device)
     def kernel(self, X, kernel_type, bw):
+        dist = 2.0 - 2.0 * X @ torch.transpose(X, 1, 0)
         if kernel_type == "gaussian":
-            return torch.exp(torch.clamp(-X / (bw ** 2) / 2, min=-75, max=75))
-        return torch.relu(3 / 4 * (1 - X / (bw ** 2)))
+            return torch.exp(torch.clamp(-dist / (bw ** 2) / 2, min=-75, max=75))
+        if kernel_type == "epa":
+            return torch.nn.functional.relu(3 / 4 * (1 - dist / (bw ** 2)))
+        raise ValueError(f"unknown kernel_type {kernel_type!r} (the reference defines 'gaussian' and 'epa')")
 
     # -- src/mean_shift.py:115-137
     def compute_bandwidth(self, X, num_samples, quantile):
         X = _lib.require_cuda(X, name="X")
         N, d = X.shape
-        if num_samples < N:  # random row subset, np RNG as in the reference (:125-128)
-            L = np.arange(N)
-            np.random.shuffle(L)
-            X = X[torch.as_tensor(L[:num_samples], device=X.device)].contiguous()
+        L = np.arange(N)
+        np.random.shuffle(L)     # always drawn, as in the reference (:125-127): NumPy's global stream stays aligned
+        if num_samples < N:      # random row subset; with num_samples >= N the reference only permutes the rows,
+            X = X[torch.as_tensor(L[:num_samples], device=X.device)].contiguous()   # which the mean does not see
             N = num_samples
         K = int(quantile * num_samples)
         kth = torch.empty(N, dtype=torch.float32, device=X.device)

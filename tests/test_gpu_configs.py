@@ -259,6 +259,7 @@ def test_c_abi_error_codes(dev):
     assert lib.sed_pipeline_run_forward(nul, nul, nul, 1, st) == -1
     h = C.c_void_p()
     assert lib.sed_pipeline_create(0, 100, 8, 8, C.byref(h)) == -1 and lib.sed_pipeline_create(1, 100, 200, 8, C.byref(h)) == -1
+    assert lib.sed_pipeline_create(1, 10001, 8, 8, C.byref(h)) == -2   # K = int(q * 10000) over all rows is the reference's only up to N = 10000
     assert lib.sed_error_string(-1).decode() == "invalid argument" and lib.sed_error_string(-2).decode().startswith("shape")
     assert lib.sed_error_string(0).decode() == "ok"
     with pytest.raises(RuntimeError):
