@@ -63,7 +63,7 @@ def graph_feature(x, idx):
     cat([x_j - x_i, x_i]) as (B, 2C, N, k)."""
     B, C, N = x.shape
     k = idx.shape[2]
-    flat = (idx + torch.arange(B).view(-1, 1, 1) * N).view(-1)     # :150-154
+    flat = (idx + torch.arange(B, device=idx.device).view(-1, 1, 1) * N).view(-1)     # :150-154
     xt = x.transpose(2, 1).contiguous()                            # :158
     nb = xt.view(B * N, C)[flat].view(B, N, k, C)                  # :161,167
     ctr = xt.view(B, N, 1, C).expand(B, N, k, C)                   # :168
@@ -127,7 +127,7 @@ def sednet_forward(sd, points, k=64, w_pos_enc=0.2, normal_metric_W=1.0, return_
                          sd["prim_encoding.0.weight"], sd["prim_encoding.0.bias"]))             # def :287-290
     x = x + w_pos_enc * pe                                                                      # :326
     emb = F.conv1d(x, sd["mlp_seg_prob2.weight"], sd["mlp_seg_prob2.bias"])                     # :329
-    out = [emb, log_prob, torch.zeros(1), edges]                                                # :335-342
+    out = [emb, log_prob, torch.zeros(1, device=emb.device), edges]                             # :335-342
     if return_intermediates:
         inter.update(x4=x4, feats=feats, x_all=x_all, x_type=x_type, type_logit=type_logit)
         return out, inter
@@ -180,9 +180,9 @@ def ms_shift(X, b, iterations, kernel_type="gaussian"):
 def ms_nms(centers, X, b):
     """src/mean_shift.py:139-179.  Returns (pruned centers, center ids (sorted), labels (N,) int64)."""
     membership = torch.min(2.0 - 2.0 * centers @ torch.transpose(X, 1, 0), 0)[1]      # :146-149
-    uniques, counts = np.unique(membership.numpy(), return_counts=True)              # :152
-    num_mem = torch.zeros(X.shape[0])
-    num_mem[uniques] = torch.from_numpy(counts.astype(np.float32))                    # :155-161
+    uniques, counts = np.unique(membership.cpu().numpy(), return_counts=True)        # :152
+    num_mem = torch.zeros(X.shape[0], device=X.device)
+    num_mem[uniques] = torch.from_numpy(counts.astype(np.float32)).to(X.device)       # :155-161
     dist = 2.0 - 2.0 * centers @ torch.transpose(centers, 1, 0)                       # :164
     nbrs = (dist < b).float()                                                         # :168-169 (b, not b**2)
     ids = torch.unique(torch.max(nbrs[uniques] * num_mem.reshape((1, -1)), 1)[1])     # :171
