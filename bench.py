@@ -366,7 +366,16 @@ def run_ours(args, rank, world, local_rank):
         for _ in range(max(args.warmup, 3)):
             step_device()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank) if (with_clocks and rank == 0) else None
+        if os.environ.get("SEDNET_BENCH_VERBOSE") and rank == 0:      # per-step device times (diagnostics, untimed)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+            evs[0].record()
+            for i in range(args.steps):
+                step_device()
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            print(f"[verbose] mode {mode} per-step ms: " + " ".join(f"{evs[i].elapsed_time(evs[i + 1]):.1f}" for i in range(args.steps)),
+                  file=sys.stderr)
+        sampler = ClockSampler(local_rank) if (with_clocks and rank == 0 and not os.environ.get("SEDNET_BENCH_NO_SAMPLER")) else None
         if sampler:
             sampler.start()
         launches(reset=True)

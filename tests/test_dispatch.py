@@ -8,12 +8,18 @@ import torch
 
 import oracle as O
 from dispatch_cases import build_case
-from util import comparable_params, flat_params, rel_err
+from util import comparable_params, cylinder_fp64, flat_params, rel_err, sign_align
 
 CASES = ("eval", "eval2", "train")
 
 
-def _check(tag, g, params, residual_of, tol, cyl_tol, res_tol):
+def _check(tag, g, params, residual_of, tol, res_tol, cyl_inputs=None):
+    """cyl_inputs (GPU runs): ids -> (points, normals, weights) of the cylinder segments.  The reference solves the
+    cylinder's circle through an FP32 explicit inverse of a cond ~ 1e6 system (src/fitting_utils.py:50-64); its own centre
+    comes out quantised to multiples of 2^-7 on noisy patches (eval2, id 1: residual 1.5e-2 where the FP64 evaluation of
+    the same formulas reaches 3.7e-3).  The kernel accumulates in FP64, so for cylinders: axis against the recorded
+    reference, centre / radius against the FP64 evaluation of the reference's formulas (tests/util.py cylinder_fp64),
+    and a residual that is not worse than the reference's."""
     ids = [int(i) for i in g[tag + "_ids"]]
     names = [str(n) for n in g[tag + "_names"]]
     assert sorted(params) == ids
@@ -27,8 +33,16 @@ def _check(tag, g, params, residual_of, tol, cyl_tol, res_tol):
         assert shapes == {"plane": [(3, 1), ()], "cone": [(1, 3), (3, 1), ()], "cylinder": [(3, 1), (1, 3), ()],
                           "sphere": [(1, 3), ()]}[name], (name, shapes)                # the reference's layouts
         got, ref = comparable_params(name, flat_params(v), g[f"{tag}_{k}_params"])
-        assert rel_err(got, ref) < (cyl_tol if name == "cylinder" else tol), (tag, k, name, got, ref)
-        assert abs(residual_of(k) - float(g[f"{tag}_{k}_residual"])) < res_tol, (tag, k, name)
+        ref_res = float(g[f"{tag}_{k}_residual"])
+        if name == "cylinder" and cyl_inputs is not None:
+            assert rel_err(got[:3], ref[:3]) < 1e-5, (tag, k, got, ref)
+            a64, c64, r64 = cylinder_fp64(*cyl_inputs[k])
+            q = flat_params(v)
+            assert rel_err(np.concatenate([sign_align(q[:3], a64), q[3:7]]), np.concatenate([a64, c64, [r64]])) < 1e-4
+            assert residual_of(k) < ref_res + 1e-5, (tag, k, residual_of(k), ref_res)
+            continue
+        assert rel_err(got, ref) < tol, (tag, k, name, got, ref)
+        assert abs(residual_of(k) - ref_res) < res_tol, (tag, k, name)
 
 
 @pytest.mark.parametrize("tag", CASES)
@@ -40,7 +54,7 @@ def test_oracle_dispatch_golden(golden, tag):
         params = O.fit_one_shape(data, W, eval=bool(mode_eval))
         dist = O.residual_loss({d[5][1]: d[3] for d in data}, params, sqrt=True)
     # the oracle equals the reference bit for bit where the vectors were recorded; 1e-5 for another CPU's BLAS
-    _check(tag, g, params, lambda k: float(dist[k][1]), 1e-5, 1e-5, 1e-6)
+    _check(tag, g, params, lambda k: float(dist[k][1]), 1e-5, 1e-6)
 
 
 @pytest.mark.gpu
@@ -56,6 +70,15 @@ def test_gpu_fit_one_shape_torch_golden(golden, tag):
     dev = torch.device("cuda", 0)
     seed, mode_eval = [int(v) for v in g[tag + "_cfg"]]
     _, _, _, _, data, W = build_case(seed, bool(mode_eval), float(g[tag + "_noise"]))
+    cyl = {}
+    for d in data:                       # the rows and weights the dispatcher hands to the cylinder fit
+        if d[2] == 4:
+            pts, nrm, w = d[0].numpy(), d[1].numpy(), None
+            if mode_eval:
+                w = (W[torch.as_tensor(d[4]), d[5][0]] + O.EPS).numpy()
+            else:
+                pts, nrm, w = pts[::2][::2], nrm[::2][::2], (W[:, d[5][0]] + O.EPS).numpy()[::2][::2]
+            cyl[d[5][1]] = (pts, nrm, w)
     data = [[d[0].to(dev), d[1].to(dev), d[2], d[3].to(dev), d[4], d[5]] for d in data]
     fitter = FittingModule("unused_closed.pth", "unused_open.pth")
     gt_points, recon = fit_one_shape_torch(data, fitter, W.to(dev), 0.1, eval=bool(mode_eval))
@@ -63,7 +86,7 @@ def test_gpu_fit_one_shape_torch_golden(golden, tag):
     assert len(recon) == len(data) and all(r is None for r in recon)
     assert all((gt_points[k] is None) == (params[k] is None) for k in params)
     dist = ResidualLoss(reduce=True).residual_loss(gt_points, params, sqrt=True)
-    _check(tag, g, params, lambda k: float(dist[k][1]), 1e-4, 3e-3, 2e-5)
+    _check(tag, g, params, lambda k: float(dist[k][1]), 1e-4, 2e-5, cyl_inputs=cyl)
 
 
 @pytest.mark.gpu
@@ -85,7 +108,10 @@ def test_gpu_fitting_module_forward_pass_golden(golden):
         assert call[l](pts.to(dev), nrm.to(dev), w, ids=ids) is None
     for k, v in fm.fitting.parameters.items():
         got, ref = comparable_params(v[0], flat_params(v), g[f"{tag}_{k}_params"])
-        assert rel_err(got, ref) < (3e-3 if v[0] == "cylinder" else 1e-4), (k, v[0], got, ref)
+        if v[0] == "cylinder":          # centre / radius: see _check; here only the axis against the recorded reference
+            assert rel_err(got[:3], ref[:3]) < 1e-5
+        else:
+            assert rel_err(got, ref) < 1e-4, (k, v[0], got, ref)
     with pytest.raises(NotImplementedError):
         fm.forward_pass_plane(data[0][0].to(dev), data[0][1].to(dev), torch.ones((data[0][0].shape[0], 1), device=dev),
                               ids=0, sample_points=True)
