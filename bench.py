@@ -365,6 +365,7 @@ def run_ours(args, rank, world, local_rank):
         step_host = lambda: pipe.run_host(P_host, N_host, QUANTILE, ITERS, mode)
         for _ in range(max(args.warmup, 3)):
             step_device()
+        gather_last()             # untimed first use: torch loads the record kernels lazily (~100 ms the first time)
         torch.cuda.synchronize()
         if os.environ.get("SEDNET_BENCH_VERBOSE") and rank == 0:      # per-step device times (diagnostics, untimed)
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
