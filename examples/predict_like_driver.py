@@ -40,21 +40,23 @@ def build_model(state, k=64):
 
 
 def predict_shape(model, model_inst, points_, normals_, labels, primitives_, quantile=0.015, iterations=50,
-                  spectral_v=None, spectral_ent=None, normal_smooth_w=0.5, chunk=1000):
-    """points_, normals_ (1,N,3) float32 host tensors; labels, primitives_ (1,N) numpy ground truth.  With spectral_v
-    (1,N,12) -- the shape's cached normal-smoothness eigenvectors -- the embedding goes through hpnet_process first
-    (HPNet_embed = True, generate_predictions_aug.py:371-378).  Returns a dict."""
+                  spectral_v=None, spectral_ent=None, normal_smooth_w=0.5, chunk=1000, hpnet_embed=False):
+    """points_, normals_ (1,N,3) float32 host tensors; labels, primitives_ (1,N) numpy ground truth.  With hpnet_embed
+    (HPNet_embed = True, the driver's default, generate_predictions_aug.py:58,371-378) the embedding goes through
+    hpnet_process first: spectral_v (1,N,12) / spectral_ent are the shape's cached normal-smoothness eigenvectors, None
+    builds them (farthest-50 table, factored affinity matrix, 10 LOBPCG steps).  Returns a dict."""
+    hpnet_embed = hpnet_embed or spectral_v is not None
     points, normals = points_.cuda(), normals_.cuda()
     with torch.no_grad():
         _input = torch.cat([points, normals], 2)                                                   # :223
         primitives_log_prob = model(_input.permute(0, 2, 1), None, False)[1]                       # :224-226
         embedding, _, _, edges_pred = model_inst(_input.permute(0, 2, 1), None, False)             # :227-229
     pred_primitives = torch.max(primitives_log_prob[0], 0)[1].data.cpu().numpy()                   # :365
-    if spectral_v is not None:
+    if hpnet_embed:
         from sednet_b200.src.smooth_normal_matrix import hpnet_process                             # src.smooth_normal_matrix
         embedding = hpnet_process(embedding.transpose(1, 2), points, normals, types=primitives_log_prob.transpose(1, 2),
                                   edges=edges_pred.transpose(1, 2), normal_smooth_w=normal_smooth_w, CHUNK=chunk,
-                                  v=spectral_v.cuda(), ent=spectral_ent)                            # :372-376
+                                  v=None if spectral_v is None else spectral_v.cuda(), ent=spectral_ent)    # :372-376
         embedding = torch.nn.functional.normalize(embedding[0], p=2, dim=1).contiguous()           # :377
     else:
         embedding = torch.nn.functional.normalize(embedding[0].T, p=2, dim=1)                      # :380
@@ -85,7 +87,8 @@ def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
     pts, nrm, lab, typ, _ = synth.make_cloud(1234, n)
     model, model_inst = build_model(synth.make_state_dict(0)), build_model(synth.make_state_dict(1, randomize_gn=True))
-    out = predict_shape(model, model_inst, torch.from_numpy(pts)[None], torch.from_numpy(nrm)[None], lab[None], typ[None])
+    out = predict_shape(model, model_inst, torch.from_numpy(pts)[None], torch.from_numpy(nrm)[None], lab[None], typ[None],
+                        hpnet_embed=True)      # HPNet_embed = True is the driver's default (generate_predictions_aug.py:58)
     print(f"segments {len(np.unique(out['cluster_ids']))}  bw {out['bw']:.4f}  s_iou {out['s_iou']:.4f}  p_iou {out['p_iou']:.4f}  "
           f"recall {out['s_recall']:.4f}")
     with tempfile.TemporaryDirectory() as d:

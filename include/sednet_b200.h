@@ -243,6 +243,26 @@ int sed_face_face_map(const float* points, const int64_t* insts, const int* idx3
  * CHUNK rows), which are divided by N * N as in the reference.  No host synchronisation. */
 int sed_compute_entropy(const float* features, int N, int K, int chunk, float* out3, sed_stream_t stream);
 
+/* knn_idx, src/smooth_normal_matrix.py:31-39: xyz (B,N,3) -> idx (B,N,k) int32, the k LARGEST entries of every row of the
+ * squared-distance matrix (-2 x.y + |x|^2 + |y|^2), largest first -- torch.topk's default largest=True makes the
+ * reference's "knn" the k FARTHEST points; kept as is.  k <= 256. */
+int sed_far_idx(const float* xyz, int B, int N, int k, int* idx, sed_stream_t stream);
+
+/* construction_affinity_matrix_normal, src/smooth_normal_matrix.py:42-92, in factored form (the reference's dense (N,N)
+ * matrix is A = (M + M^T) / 2, M_ij = a_ij / sqrt(D_i D_j), a_ij = w_ij at the k scattered entries of row i where
+ * w_ij != 0 and 1e-12 everywhere else, D_i = sum_j a_ij):  normals (B,N,3), idx (B,N,k) from sed_far_idx ->
+ * w (B,N,k) = exp(-acos(clamp(n_i.n_j, -0.99, 0.99))^2 / (2 sigma^2)), dinv (B,N) = 1 / sqrt(D_i). */
+int sed_affinity_normal_build(const float* normals, const int* idx, int B, int N, int k, float sigma, float* w, float* dinv,
+                              sed_stream_t stream);
+
+/* Block product with that matrix for ONE cloud (what torch.lobpcg needs from it, :191): prepare builds the transposed
+ * adjacency in `workspace` (sed_affinity_workspace_bytes(N,k) bytes) once; matmul computes Y (N,m) = A X for X (N,m)
+ * row-major, m <= 64.  idx (N,k), w (N,k), dinv (N) of that cloud. */
+int64_t sed_affinity_workspace_bytes(int N, int k);
+int sed_affinity_prepare(const int* idx, const float* w, int N, int k, void* workspace, sed_stream_t stream);
+int sed_affinity_matmul(const int* idx, const float* w, const float* dinv, void* workspace, const float* X, int N, int k, int m,
+                        float* Y, sed_stream_t stream);
+
 /* ------------------------------------------------------------------ evaluation (src/segment_utils.py, src/utils.py) */
 
 /* The integer tables from which the driver's matching / IoU metrics are computed (SIOU_matched_segments[_usecd]

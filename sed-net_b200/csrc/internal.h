@@ -11,6 +11,7 @@ int knn_l2(const float* x, long long bstride, int B, int C, int N, int k, void* 
            int sorted = 1);
 int knn_pn(const float* x6, long long bstride, int B, int N, int k, float W, void* idx, int idx64, cudaStream_t st,
            int sorted = 1);
+int knn_far(const float* x, long long bstride, int B, int C, int N, int k, void* idx, int idx64, cudaStream_t st);
 int nearest_cos(const float* Q, const float* Cand, int B, int Nq, int Nc, const int* nc_ptr, int d, void* out,
                 int idx64, cudaStream_t st);
 

@@ -13,7 +13,7 @@
 
 namespace sed {
 
-enum { M_L2 = 0, M_PN = 1, M_COS = 2 };
+enum { M_L2 = 0, M_PN = 1, M_COS = 2, M_FAR = 3 };
 enum { L_CHANNEL_MAJOR = 0, L_ROW_MAJOR = 1 };
 
 constexpr int KNN_THREADS = 256;
@@ -132,6 +132,9 @@ __device__ __forceinline__ float metric_score(float dot, float dot2, float xxq, 
         float pd = __fadd_rn(__fsub_rn(xxc, 2.0f * dot), xxq);
         float nd = __fsub_rn(2.0f, 2.0f * dot2);
         return -__fmul_rn(pd, __fadd_rn(1.0f, __fmul_rn(nd, W)));
+    } else if (METRIC == M_FAR) {
+        // src/smooth_normal_matrix.py:25-28,35-37: dist = -2 x.y ; dist += |x|^2 ; dist += |y|^2 ; topk keeps the LARGEST
+        return __fadd_rn(__fadd_rn(-2.0f * dot, xxq), xxc);
     } else {
         // src/mean_shift.py:130,146: dist = 2 - 2 x.y ; score = -dist
         return -__fsub_rn(2.0f, 2.0f * dot);
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(KNN_THREADS, 1) knn_kernel(KnnParams p) {
     const int C = p.C;
     const int Cp = ((C + CK - 1) / CK) * CK;
     const int nchunk = Cp / CK;
-    const int normC = (METRIC == M_L2) ? C : (METRIC == M_PN ? 3 : 0);
+    const int normC = (METRIC == M_L2 || METRIC == M_FAR) ? C : (METRIC == M_PN ? 3 : 0);
 
     float* Qs = reinterpret_cast<float*>(smem_raw);  // [Cp][TQ]
     float* Xs = Qs + Cp * TQ;                         // [2][CK][TC]
@@ -445,6 +448,16 @@ int knn_pn(const float* x6, long long bstride, int B, int N, int k, float W, voi
     p.xq = p.xc = x6; p.q_bstride = p.c_bstride = bstride; p.ldq = p.ldc = N;
     p.C = 6; p.Nq = p.Nc = N; p.k = k; p.W = W; p.out_idx = idx; p.idx64 = idx64;
     return dispatch_knn_idx<M_PN, L_CHANNEL_MAJOR>(p, B, st);
+}
+
+// The k FARTHEST points of every point (largest squared distance first): the reference's knn_idx, whose topk keeps the
+// largest entries of the distance matrix (src/smooth_normal_matrix.py:31-39).  x channel-major (B,C,N), k <= 256.
+int knn_far(const float* x, long long bstride, int B, int C, int N, int k, void* idx, int idx64, cudaStream_t st) {
+    if (!x || !idx || B <= 0 || C <= 0 || C > 256 || N < k || k <= 0) return SED_ERR_ARG;
+    KnnParams p{};
+    p.xq = p.xc = x; p.q_bstride = p.c_bstride = bstride; p.ldq = p.ldc = N;
+    p.C = C; p.Nq = p.Nc = N; p.k = k; p.W = 0.f; p.out_idx = idx; p.idx64 = idx64;
+    return dispatch_knn_idx<M_FAR, L_CHANNEL_MAJOR>(p, B, st);
 }
 
 // Nearest candidate (cosine distance 2 - 2 q.c, lowest index on ties) for every query row.

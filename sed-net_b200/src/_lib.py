@@ -42,6 +42,11 @@ SIGNATURES = {
     "sed_inst_edges": (I, [c_i32p, c_i64p, I, I, c_vp, c_vp]),
     "sed_face_face_map": (I, [c_f32p, c_i64p, c_i32p, c_i64p, I, I, I, c_vp, c_vp]),
     "sed_compute_entropy": (I, [c_f32p, I, I, I, c_f32p, c_vp]),
+    "sed_far_idx": (I, [c_f32p, I, I, I, c_i32p, c_vp]),
+    "sed_affinity_normal_build": (I, [c_f32p, c_i32p, I, I, I, F, c_f32p, c_f32p, c_vp]),
+    "sed_affinity_workspace_bytes": (L, [I, I]),
+    "sed_affinity_prepare": (I, [c_i32p, c_f32p, I, I, c_vp, c_vp]),
+    "sed_affinity_matmul": (I, [c_i32p, c_f32p, c_f32p, c_vp, c_f32p, I, I, I, c_f32p, c_vp]),
     "sed_segment_tables": (I, [c_i64p, c_i64p, c_i64p, c_i64p, I, I, I, I, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p,
                                c_vp]),
     "sed_type_vote_weighted": (I, [c_i64p, c_f32p, I, I, I, c_f32p, c_vp]),

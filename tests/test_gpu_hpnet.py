@@ -50,8 +50,7 @@ def test_compute_entropy_and_hpnet_golden(dev, tmp_path):
         ref = g[f"c{case}_emb_sample"]
         assert np.abs(emb[0, ::50].cpu().numpy() - ref).max() < 2e-5 * np.abs(ref).max()
         assert abs(float(emb.double().sum()) - float(g[f"c{case}_emb_sum"])) < 1e-4 * abs(float(g[f"c{case}_emb_sum"]))
-    with pytest.raises(NotImplementedError):
-        snm.hpnet_process(feat.to(dev), None, None, id=None)            # no cache, no v: the lobpcg branch is not built
+    # (no cache, no v: the branch that builds the spectral vectors -- tests/test_hpnet_spectral.py)
     with torch.no_grad():
         e_o = float(OH.compute_entropy(types.exp(), CHUNK=chunk))
     assert abs(float(snm.compute_entropy(types.exp().to(dev), CHUNK=chunk)) - e_o) < 1e-5 * e_o     # K = 6

@@ -1,0 +1,178 @@
+"""The branch of hpnet_process that BUILDS the spectral vectors (reference src/smooth_normal_matrix.py:31-92, 190-196):
+farthest-50 index table, normal-affinity matrix, torch.lobpcg(k=12, niter=10), row normalisation, entropy, concatenation.
+tests/golden/hpnet_spectral.npz was recorded from the UNMODIFIED reference (oracle/make_golden_hpnet.py --spectral) with the
+eigen-iteration's start block drawn right after torch.manual_seed(seed), so it can be rebuilt here.
+
+Eigenvector columns are compared up to sign (LAPACK / cuSOLVER pick it; everything downstream -- row norms, pairwise
+distances, compute_entropy -- is invariant to it)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle as O
+import oracle_hpnet as OH
+from sednet_b200 import synth
+from util import canon, knn_set_agreement
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _case(seed, n):
+    p, nrm, lab, typ, _ = synth.make_cloud(seed, n)
+    feat = torch.from_numpy(synth.make_embedding(lab, 128, 0.05, seed))[None] * 3.0
+    g = torch.Generator().manual_seed(seed + 100)
+    types = torch.log_softmax(2.0 * torch.randn((1, n, 6), generator=g), -1)
+    edges = torch.randn((1, n, 2), generator=g)
+    torch.manual_seed(seed)
+    X0 = torch.randn((n, 12))
+    return torch.from_numpy(p)[None], torch.from_numpy(nrm)[None], feat, types, edges, X0, lab
+
+
+def _align_signs(v, ref):
+    s = torch.sign((v * ref).sum(0))
+    s[s == 0] = 1
+    return v * s
+
+
+def _subspace_angles(U, V):
+    Qu, _ = torch.linalg.qr(U.double())
+    Qv, _ = torch.linalg.qr(V.double())
+    return torch.acos(torch.linalg.svdvals(Qu.T @ Qv).clamp(max=1.0))
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_oracle_spectral_golden(golden, case):
+    g = golden("hpnet_spectral")
+    seed, n, chunk = [int(v) for v in g[f"s{case}_cfg"]]
+    P, Nn, feat, types, edges, X0, _ = _case(seed, n)
+    with torch.no_grad():
+        idx = OH.knn_idx(P, 50)
+        A = OH.construction_affinity_matrix_normal(P, Nn)
+        v, E = OH.spectral_vectors(P, Nn, X0[None])
+        ent = OH.compute_entropy(v, chunk)
+        emb = OH.hpnet_combine(feat, v, ent, types, edges, 0.5, chunk)
+    assert np.array_equal(idx[0, ::37].numpy(), g[f"s{case}_idx_sample"])
+    assert np.abs(A[0, ::50, ::3].numpy() - g[f"s{case}_A_sample"]).max() <= 1e-6 * float(A.max())
+    assert abs(float(A[0].double().pow(2).sum().sqrt()) - float(g[f"s{case}_A_fro"])) < 1e-6 * float(g[f"s{case}_A_fro"])
+    vr = torch.from_numpy(g[f"s{case}_v"])
+    assert float((_align_signs(v[0], vr) - vr).abs().max()) < 1e-4
+    assert abs(float(ent) - float(g[f"s{case}_ent"])) < 1e-5
+    assert np.abs(emb[0, ::25].numpy() - g[f"s{case}_emb_sample"]).max() < 1e-4
+
+
+def test_lobpcg_restatement_matches_torch_lobpcg():
+    """Host logic of the product (device-agnostic): lobpcg_top, the restatement of torch.lobpcg's "ortho" method around a
+    block product, against torch.lobpcg itself on the oracle's dense affinity matrix, same start block, for 1, 2, 3 and 10
+    steps (niter = 1 exposes torch's quirk of returning E = 0 after the initial Rayleigh-Ritz step)."""
+    from sednet_b200.src.smooth_normal_matrix import lobpcg_top
+    P, Nn, _, _, _, X0, _ = _case(11, 1500)
+    with torch.no_grad():
+        A = OH.construction_affinity_matrix_normal(P, Nn)[0]
+        for niter in (1, 2, 3, 10):
+            E1, V1 = torch.lobpcg(A, k=12, niter=niter, X=X0.clone())
+            E2, V2 = lobpcg_top(lambda Y: A @ Y, A.shape[0], 12, niter, X0.clone())
+            assert float((E1 - E2).abs().max()) <= 1e-5 * max(float(E1.abs().max()), 1.0), niter
+            # the leading vectors agree to FP32 noise; the last two of the block (Ritz values 1 % apart from the next ones
+            # outside it, least converged after 10 steps) amplify that noise to ~5e-3
+            ang = _subspace_angles(V1, V2)
+            assert float(ang.max()) < 2e-2 and float(_subspace_angles(V1[:, :8], V2[:, :8]).max()) < 2e-3, (niter, ang)
+            d = (_align_signs(V2, V1) - V1).abs()
+            assert float(d[:, :8].max()) < 2e-3 and float(d.max()) < 2e-2, niter
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    from sednet_b200.src import _lib
+    _lib.load()
+    return torch.device("cuda", 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [0, 1])
+def test_gpu_farthest_table_and_affinity_operator(dev, golden, case):
+    """knn_idx (farthest-50), the factored affinity matrix and its block product against the oracle's dense tensors."""
+    from sednet_b200.src import smooth_normal_matrix as snm
+    g = golden("hpnet_spectral")
+    seed, n, chunk = [int(v) for v in g[f"s{case}_cfg"]]
+    P, Nn, _, _, _, X0, _ = _case(seed, n)
+    idx = snm.knn_idx(P.to(dev), 50).cpu()
+    with torch.no_grad():
+        idx_ref = OH.knn_idx(P, 50)
+        A_ref = OH.construction_affinity_matrix_normal(P, Nn)[0]
+    rows, shared = knn_set_agreement(idx.numpy(), idx_ref.numpy())
+    assert rows >= 0.995 and shared >= 0.9999, (rows, shared)      # FP32 near-ties of the 50th-farthest distance only
+    assert (idx[0, :, 0] == idx_ref[0, :, 0]).float().mean() > 0.999          # farthest first
+    op = snm.construction_affinity_matrix_normal(P.to(dev), Nn.to(dev), sigma=0.1, knn=50)
+    A = op.to_dense()[0].cpu()
+    scale = float(A_ref.abs().max())
+    # rows whose farthest-50 set differs at a near-tie carry a different (equally valid) scattered entry: compare the rest
+    same = torch.from_numpy((np.sort(idx[0].numpy(), 1) == np.sort(idx_ref[0].numpy(), 1)).all(1))
+    m = same[:, None] & same[None, :]
+    assert float(((A - A_ref).abs() * m).max()) < 2e-5 * scale
+    assert abs(float(A.double().pow(2).sum().sqrt()) / float(g[f"s{case}_A_fro"]) - 1) < 1e-2
+    # block product of the factored operator == dense product with the operator's own dense form
+    Y = op.matmul(0, X0.to(dev)).cpu()
+    Yd = (A.double() @ X0.double()).float()
+    assert float((Y - Yd).abs().max()) < 1e-5 * float(Yd.abs().max())
+    X36 = torch.randn((n, 36), generator=torch.Generator().manual_seed(1))
+    Y36 = op.matmul(0, X36.to(dev)).cpu()
+    assert float((Y36 - (A.double() @ X36.double()).float()).abs().max()) < 1e-5 * float(Y36.abs().max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [0, 1])
+def test_gpu_hpnet_process_builds_spectral_vectors(dev, golden, case, tmp_path, monkeypatch):
+    """hpnet_process without a cache (the driver's default on a fresh shape): same start block as the recorded reference
+    run -> spectral vectors up to column sign, their entropy, and the weighted 148-column concatenation."""
+    from sednet_b200.src import smooth_normal_matrix as snm
+    g = golden("hpnet_spectral")
+    seed, n, chunk = [int(v) for v in g[f"s{case}_cfg"]]
+    P, Nn, feat, types, edges, X0, _ = _case(seed, n)
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("src/normal_smooth_cache")
+    emb = snm.hpnet_process(feat.to(dev), P.to(dev), Nn.to(dev), id=5, types=types.to(dev), edges=edges.to(dev),
+                            normal_smooth_w=0.5, CHUNK=chunk, X=X0[None])
+    assert emb.shape == (1, n, 148)
+    v = torch.load("src/normal_smooth_cache/Us_5_0.1_50.pt").cpu()[0]          # the cache the reference would write
+    vr = torch.from_numpy(g[f"s{case}_v"])
+    ang = _subspace_angles(v, vr)
+    assert float(ang.max()) < 2e-2 and float(_subspace_angles(v[:, :8], vr[:, :8]).max()) < 5e-3, ang
+    va = _align_signs(v, vr)
+    assert float((va - vr).abs().max()) < 2e-2 and float((va - vr).abs().mean()) < 1e-4
+    ent = float(torch.load("src/normal_smooth_cache/WUs_5_0.1_50.pt"))
+    assert abs(ent - float(g[f"s{case}_ent"])) < 2e-4
+    ref = torch.from_numpy(g[f"s{case}_emb_sample"])
+    got = emb[0, ::25].cpu()
+    assert float((got[:, :128] - ref[:, :128]).abs().max()) < 1e-4          # features x (1.7 - entropy)
+    assert float((got[:, 140:] - ref[:, 140:]).abs().max()) < 1e-4          # type / edge probabilities x (0.25 - entropy)
+    assert float((got[:, 128:140].abs() - ref[:, 128:140].abs()).abs().max()) < 2e-3
+    # second call: the cache is found and gives the same embedding
+    emb2 = snm.hpnet_process(feat.to(dev), P.to(dev), Nn.to(dev), id=5, types=types.to(dev), edges=edges.to(dev),
+                             normal_smooth_w=0.5, CHUNK=chunk)
+    assert float((emb2 - emb).abs().max()) < 1e-6
+
+
+@pytest.mark.gpu
+def test_gpu_hpnet_then_meanshift_labels_match_oracle_chain(dev):
+    """The driver's sequence on a fresh shape (generate_predictions_aug.py:371-387): hpnet_process (spectral vectors built,
+    148 columns) -> normalise -> mean-shift.  Labels against the oracle chain (dense affinity + torch.lobpcg + oracle
+    mean-shift) on the same start block."""
+    from sednet_b200.src import smooth_normal_matrix as snm
+    from sednet_b200.src.mean_shift import MeanShift
+    seed, n, chunk = 21, 2400, 480
+    P, Nn, feat, types, edges, X0, lab = _case(seed, n)
+    emb = snm.hpnet_process(feat.to(dev), P.to(dev), Nn.to(dev), id=None, types=types.to(dev), edges=edges.to(dev),
+                            normal_smooth_w=0.5, CHUNK=chunk, X=X0[None])
+    e = torch.nn.functional.normalize(emb[0], p=2, dim=1)
+    newX, center, bw, labels = MeanShift().mean_shift(e, 10000, 0.015, 20)
+    with torch.no_grad():
+        v, _ = OH.spectral_vectors(P, Nn, X0[None])
+        emb_o = OH.hpnet_combine(feat, v, OH.compute_entropy(v, chunk), types, edges, 0.5, chunk)
+        eo = torch.nn.functional.normalize(emb_o[0], p=2, dim=1)
+        _, _, obw, olab = O.mean_shift(eo, 10000, 0.015, 20)
+    assert (canon(labels.cpu().numpy()) == canon(olab.numpy())).all()
+    assert abs(float(bw) - float(obw)) < 1e-3 * float(obw)
