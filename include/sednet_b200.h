@@ -299,6 +299,12 @@ int sed_lstsq3(const float* A, const float* Y, int m, float* x, int* status, sed
  * descending and right singular vectors V (3,3) as columns (sign of each column is arbitrary, as in LAPACK). */
 int sed_svd3(const float* A, int m, float* S, float* V, sed_stream_t stream);
 
+/* CustomSVD.backward (src/fitting_utils.py:385-417, :449-452; only grad_V flows back, as in the reference): U (m,3), S (3),
+ * V (3,3) of the forward, grad_V (3,3) -> grad_input (m,3) = 2 U diag(S) sym(K^T o (V^T grad_V)) V^T with svd_grad_K's 1e-6
+ * floor on |S_i - S_j|. */
+int sed_svd3_backward(const float* U, const float* S, const float* V, const float* grad_V, int m, float* grad_input,
+                      sed_stream_t stream);
+
 /* ResidualLoss.residual_loss(points, parameters, sqrt) with reduce=True, src/primitives.py:36-44 over
  * ComputePrimitiveDistance.distance_from_* :89-195: mean (guarded-sqrt) distance of each segment's points to
  * its fitted primitive.  residual (B,S) f32 (0 for skipped segments). */

@@ -320,6 +320,26 @@ def fit_cone(points, normals, weights):
     return c, a, torch.clamp(theta, min=1e-3, max=3.142 / 2 - 1e-3)                  # :846
 
 
+
+def svd_grad_K(S):
+    """src/fitting_utils.py:394-417."""
+    N = S.shape[0]
+    s1, s2 = S.view((1, N)), S.view((N, 1))
+    diff, plus = s2 - s1, s2 + s1
+    K_neg = torch.sign(diff) * torch.max(torch.abs(diff), torch.ones((N, N)) * 10 ** (-6))
+    K_neg[torch.arange(N), torch.arange(N)] = 10 ** (-6)
+    return (1 / K_neg) * (1 / plus) * (torch.ones((N, N)) - torch.eye(N))
+
+
+def compute_grad_V(U, S, V, grad_V):
+    """src/fitting_utils.py:385-391: the backward of customsvd (only grad_V flows back, :449-452)."""
+    N = S.shape[0]
+    K = svd_grad_K(S)
+    Sm = torch.eye(N) * S.reshape((N, 1))
+    inner = K.T * (V.T @ grad_V)
+    inner = (inner + inner.T) / 2.0
+    return 2 * U @ Sm @ inner @ V.T
+
 # --------------------------------------------------------------------------
 # point -> primitive distances -- src/primitives.py
 # --------------------------------------------------------------------------

@@ -11,6 +11,8 @@
 //   * singular values (rank test, condition number)   = sqrt of its eigenvalues;
 //   * the QR least-squares solution                    = (A^T A)^-1 A^T Y  (full rank), and the reference's
 //     regularised branch is literally (A^T A + lambda I)^-1 A^T Y with lambda from the 1e-6 * 10^i ladder.
+#include <algorithm>
+
 #include "internal.h"
 
 namespace sed {
@@ -605,6 +607,55 @@ __global__ void __launch_bounds__(FIT_THREADS) svd3_kernel(const float* __restri
     if (threadIdx.x < 9) V[threadIdx.x] = (float)Vd[threadIdx.x / 3][threadIdx.x % 3];
 }
 
+// CustomSVD.backward (src/fitting_utils.py:385-417, :449-452): only grad_V flows back,
+//     grad_input = 2 U diag(S) sym(K^T o (V^T grad_V)) V^T,   K_ij = 1 / ((S_i - S_j)(S_i + S_j)) off the diagonal, with
+//     |S_i - S_j| floored at 1e-6 (svd_grad_K).  The 3 x 3 factor is formed per thread in FP32 in the reference's operation
+//     order; every thread then multiplies its rows of U by it.
+__global__ void __launch_bounds__(256) svd3_backward_kernel(const float* __restrict__ U, const float* __restrict__ S,
+                                                            const float* __restrict__ V, const float* __restrict__ gV, int m,
+                                                            float* __restrict__ gin) {
+    float s[3], v[3][3], g[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        s[i] = S[i];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { v[i][j] = V[3 * i + j]; g[i][j] = gV[3 * i + j]; }
+    }
+    float K[3][3], inner[3][3], W[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float diff = s[i] - s[j];                                  // s2 - s1: row index first
+            const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);
+            float kneg = sgn * fmaxf(fabsf(diff), 1e-6f);
+            if (i == j) kneg = 1e-6f;
+            K[i][j] = (i == j) ? 0.f : (1.0f / kneg) * (1.0f / (s[i] + s[j]));   // K_neg * K_pos * rm_diag
+        }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float vtg = v[0][i] * g[0][j] + v[1][i] * g[1][j] + v[2][i] * g[2][j];   // (V^T grad_V)_ij
+            inner[i][j] = K[j][i] * vtg;                                                    // K.T * (...)
+        }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            // (S inner_sym V^T)_ij = s_i sum_c sym_ic V_jc
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) acc += ((inner[i][c] + inner[c][i]) / 2.0f) * v[j][c];
+            W[i][j] = 2.0f * s[i] * acc;
+        }
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < m; r += gridDim.x * blockDim.x) {
+        const float u0 = U[3 * r], u1 = U[3 * r + 1], u2 = U[3 * r + 2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gin[3 * r + j] = u0 * W[0][j] + u1 * W[1][j] + u2 * W[2][j];
+    }
+}
+
 // ---- point -> primitive distances, FP32 in the reference's operation order (src/primitives.py)
 __device__ __forceinline__ float guard_sqrtf(float x) { return sqrtf(fmaxf(x, 1e-5f)); }  // src/guard.py:12-14
 
@@ -765,6 +816,14 @@ int sed_lstsq3(const float* A, const float* Y, int m, float* x, int* status, sed
 int sed_svd3(const float* A, int m, float* S, float* V, sed_stream_t stream) {
     if (!A || !S || !V || m <= 0) return SED_ERR_ARG;
     svd3_kernel<<<1, FIT_THREADS, 0, (cudaStream_t)stream>>>(A, m, S, V);
+    SED_CHECK_LAUNCH();
+    return SED_OK;
+}
+
+int sed_svd3_backward(const float* U, const float* S, const float* V, const float* grad_V, int m, float* grad_input,
+                      sed_stream_t stream) {
+    if (!U || !S || !V || !grad_V || !grad_input || m <= 0) return SED_ERR_ARG;
+    svd3_backward_kernel<<<std::min((m + 255) / 256, 4 * kNumSMs), 256, 0, (cudaStream_t)stream>>>(U, S, V, grad_V, m, grad_input);
     SED_CHECK_LAUNCH();
     return SED_OK;
 }

@@ -459,6 +459,17 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     return v;
 }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+// The prune-booking words are shared between warps without a barrier on purpose (a hint that arrives late only moves a
+// prune to a later tile).  Relaxed CTA-scope atomics make that a well-defined (morally strong) access pair in the PTX memory
+// model instead of a data race; they compile to the same LDS / STS.
+__device__ __forceinline__ uint32_t hint_load(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.relaxed.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void hint_store(uint32_t a, uint32_t v) {
+    asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
     asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t; }" ::"r"(a), "r"(v));
 }
@@ -779,16 +790,16 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
             // CTA-wide prunes: the four warps share the TMEM ring, so a warp that prunes alone stalls the others after
             // ~2 tiles.  A warp whose buffers pass the soft mark books a prune SS_LAG tiles ahead (further than the
             // warps can drift apart); every warp prunes when it reaches the booked tile.  The private prune of
-            // maybe_prune() stays as the overflow guard.  The booking words are plain shared-memory hints written and
-            // polled without synchronisation on purpose (compute-sanitizer racecheck reports them): a missed hint only
-            // moves a warp's prune to a later tile, and the result does not depend on when a row is pruned.
-            if (lds_u32(sched_addr + (uint32_t)(j & 15) * 4u) == (uint32_t)j) {
+            // maybe_prune() stays as the overflow guard.  The booking words are hints written and polled without a barrier
+            // on purpose, through relaxed CTA-scope atomics (hint_load / hint_store): a missed hint only moves a warp's
+            // prune to a later tile, and the result does not depend on when a row is pruned.
+            if (hint_load(sched_addr + (uint32_t)(j & 15) * 4u) == (uint32_t)j) {
                 ss_prune<true>(key_addr, idx_addr, SS_CAP, k, p.win, cnt, thr);
             } else if (__any_sync(0xffffffffu, cnt > p.soft)) {
                 bool booked = false;
 #pragma unroll
-                for (int d = 1; d <= SS_LAG; ++d) booked |= lds_u32(sched_addr + (uint32_t)((j + d) & 15) * 4u) == (uint32_t)(j + d);
-                if (!booked && lane == 0) sts_u32(sched_addr + (uint32_t)((j + SS_LAG) & 15) * 4u, (uint32_t)(j + SS_LAG));
+                for (int d = 1; d <= SS_LAG; ++d) booked |= hint_load(sched_addr + (uint32_t)((j + d) & 15) * 4u) == (uint32_t)(j + d);
+                if (!booked && lane == 0) hint_store(sched_addr + (uint32_t)((j + SS_LAG) & 15) * 4u, (uint32_t)(j + SS_LAG));
             }
             maybe_prune();
             process(a0, a1, j * SS_NC, xcs);
@@ -1058,13 +1069,13 @@ kth_stream_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_const
             tmem_ld32(sb + 64 + 32, b1);
             // CTA-wide booked prunes (see select_stream_kernel): the four warps share the TMEM ring, so they prune together
             if (p.soft > 0) {
-                if (lds_u32(sched_addr + (uint32_t)(j & 15) * 4u) == (uint32_t)j) {
+                if (hint_load(sched_addr + (uint32_t)(j & 15) * 4u) == (uint32_t)j) {
                     ss_prune<false>(key_addr, 0u, KS_CAP, k, p.win, cnt, thr);
                 } else if (__any_sync(0xffffffffu, cnt > p.soft)) {
                     bool booked = false;
 #pragma unroll
-                    for (int d = 1; d <= SS_LAG; ++d) booked |= lds_u32(sched_addr + (uint32_t)((j + d) & 15) * 4u) == (uint32_t)(j + d);
-                    if (!booked && lane == 0) sts_u32(sched_addr + (uint32_t)((j + SS_LAG) & 15) * 4u, (uint32_t)(j + SS_LAG));
+                    for (int d = 1; d <= SS_LAG; ++d) booked |= hint_load(sched_addr + (uint32_t)((j + d) & 15) * 4u) == (uint32_t)(j + d);
+                    if (!booked && lane == 0) hint_store(sched_addr + (uint32_t)((j + SS_LAG) & 15) * 4u, (uint32_t)(j + SS_LAG));
                 }
             }
             maybe_prune();

@@ -54,6 +54,7 @@ SIGNATURES = {
     "sed_matched_chamfer": (I, [c_f32p, c_i64p, c_i64p, c_i32p, c_i32p, I, I, I, c_f32p, c_f32p, c_vp]),
     "sed_lstsq3": (I, [c_f32p, c_f32p, I, c_f32p, c_i32p, c_vp]),
     "sed_svd3": (I, [c_f32p, I, c_f32p, c_f32p, c_vp]),
+    "sed_svd3_backward": (I, [c_f32p, c_f32p, c_f32p, c_f32p, I, c_f32p, c_vp]),
     "sed_residual_segments": (I, [c_f32p, c_i64p, c_i32p, c_f32p, c_i32p, I, I, I, I, c_f32p, c_vp]),
     "sed_primitive_distance": (I, [c_f32p, I, I, c_f32p, I, c_f32p, c_vp]),
     "sed_segment_types": (I, [c_f32p, c_i64p, I, I, I, I, c_i32p, c_i32p, c_i32p, c_vp]),

@@ -1,5 +1,5 @@
 """Hot-path subset of reference src/fitting_utils.py: LeastSquares.lstsq / best_lambda (:32-85), customsvd forward
-(:420-455) and weights_normalize (:306-325), on the sm_100a fit kernels (FP64 moment accumulation + 3x3 Jacobi)."""
+with its custom backward (:385-455) and weights_normalize (:306-325), on the sm_100a fit kernels (FP64 moment accumulation + 3x3 Jacobi)."""
 import numpy as np
 import torch
 
@@ -29,7 +29,7 @@ class LeastSquares:
 
 def best_lambda(A):
     """src/fitting_utils.py:68-85 for a symmetric 3x3 A: smallest 1e-6 * 10^i with A + lambda I of full rank."""
-    _, S, _ = customsvd(_lib.require_cuda(A, name="A"))
+    _, S, _ = _svd3_forward(A)
     s_max, s_min = float(S[0]), float(S[-1])   # singular values of a symmetric PSD matrix = eigenvalues
     lamb = 1e-6
     for _ in range(7):
@@ -39,8 +39,7 @@ def best_lambda(A):
     return lamb
 
 
-def customsvd(x):
-    """Forward of CustomSVD (src/fitting_utils.py:420-455; torch.svd(some=True)) for an (m,3) matrix: U, S, V."""
+def _svd3_forward(x):
     x = _lib.require_cuda(x, name="x")
     if x.dim() != 2 or x.shape[1] != 3:
         raise NotImplementedError("customsvd is implemented for (m, 3) matrices, the only shape on the fitting path")
@@ -49,6 +48,31 @@ def customsvd(x):
     _lib.call("sed_svd3", _lib.ptr(x), x.shape[0], _lib.ptr(S), _lib.ptr(V), _lib.stream())
     U = (x @ V) / torch.clamp(S, min=1e-30)
     return U, S, V
+
+
+class CustomSVD(torch.autograd.Function):
+    """src/fitting_utils.py:420-452: forward = torch.svd(input, some=True) of an (m,3) matrix; backward lets only grad_V flow
+    back (compute_grad_V / svd_grad_K, :385-417), with |S_i - S_j| floored at 1e-6 so equal singular values do not blow up."""
+
+    @staticmethod
+    def forward(ctx, input):
+        U, S, V = _svd3_forward(input.detach())
+        ctx.save_for_backward(U, S, V)
+        return U, S, V
+
+    @staticmethod
+    def backward(ctx, grad_U, grad_S, grad_V):
+        U, S, V = ctx.saved_tensors
+        if grad_V is None:
+            return torch.zeros_like(U)
+        gV = _lib.require_cuda(grad_V, name="grad_V")
+        gin = torch.empty_like(U)
+        _lib.call("sed_svd3_backward", _lib.ptr(U.contiguous()), _lib.ptr(S), _lib.ptr(V), _lib.ptr(gV), U.shape[0],
+                  _lib.ptr(gin), _lib.stream())
+        return gin
+
+
+customsvd = CustomSVD.apply
 
 
 def weights_normalize(weights, bw):
