@@ -460,18 +460,16 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
 }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 // The prune-booking words are shared between warps without a barrier on purpose (a hint that arrives late only moves a
-// prune to a later tile).  Relaxed CTA-scope atomics make that a well-defined (morally strong) access pair in the PTX memory
-// model instead of a data race; they compile to the same LDS / STS.
+// prune to a later tile).  They are read and written with shared-memory atomics -- one lane per warp, the value broadcast
+// by a shuffle -- so that concurrent access is well defined (and compute-sanitizer's racecheck has nothing to report).
 __device__ __forceinline__ uint32_t hint_load(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.relaxed.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
+    uint32_t v = 0;
+    if ((threadIdx.x & 31) == 0) asm volatile("atom.shared.or.b32 %0, [%1], 0;" : "=r"(v) : "r"(a) : "memory");
+    return __shfl_sync(0xffffffffu, v, 0);
 }
 __device__ __forceinline__ void hint_store(uint32_t a, uint32_t v) {
-    asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
-__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
-    asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t; }" ::"r"(a), "r"(v));
+    uint32_t old;
+    asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(v) : "memory");
 }
 template <int NS>
 __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {   // producer-side wait: back off
@@ -791,7 +789,7 @@ select_stream_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_co
             // ~2 tiles.  A warp whose buffers pass the soft mark books a prune SS_LAG tiles ahead (further than the
             // warps can drift apart); every warp prunes when it reaches the booked tile.  The private prune of
             // maybe_prune() stays as the overflow guard.  The booking words are hints written and polled without a barrier
-            // on purpose, through relaxed CTA-scope atomics (hint_load / hint_store): a missed hint only moves a warp's
+            // on purpose, through shared-memory atomics (hint_load / hint_store): a missed hint only moves a warp's
             // prune to a later tile, and the result does not depend on when a row is pruned.
             if (hint_load(sched_addr + (uint32_t)(j & 15) * 4u) == (uint32_t)j) {
                 ss_prune<true>(key_addr, idx_addr, SS_CAP, k, p.win, cnt, thr);

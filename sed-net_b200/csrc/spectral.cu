@@ -93,15 +93,14 @@ __global__ void aff_fill_kernel(const int* __restrict__ idx, const float* __rest
     src[pos] = (int)(e / k);
     val[pos] = v;
 }
-// one warp per row: order the row's (source, value) pairs by source (sources are distinct: a row scatters to k distinct
-// columns).  Rank sort: every element counts the smaller sources of its row.
+// one CTA per row: order the row's (source, value) pairs by source (sources are distinct: a row scatters to k distinct
+// columns).  Rank sort: every element counts the smaller sources of its row -- O(L^2 / 256) per row; the farthest-point
+// tables concentrate on a few extreme points, whose in-lists can hold thousands of entries, hence a whole CTA per row.
 __global__ void __launch_bounds__(256) aff_sort_kernel(const int* __restrict__ start, int N, const int* __restrict__ src,
                                                        const float* __restrict__ val, int* __restrict__ src_o, float* __restrict__ val_o) {
-    const int lane = threadIdx.x & 31;
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (i >= N) return;
+    const int i = blockIdx.x;
     const int lo = start[i], hi = start[i + 1];
-    for (int a = lo + lane; a < hi; a += 32) {
+    for (int a = lo + threadIdx.x; a < hi; a += 256) {
         const int s = src[a];
         int r = 0;
         for (int c = lo; c < hi; ++c) r += (src[c] < s) ? 1 : 0;
@@ -230,7 +229,7 @@ int sed_affinity_prepare(const int* idx, const float* w, int N, int k, void* wor
     aff_count_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(idx, w, N, k, a.cnt);
     aff_scan_kernel<<<1, 1024, 0, st>>>(a.cnt, N, a.start, a.cursor);
     aff_fill_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(idx, w, N, k, a.cursor, a.src_tmp, a.val_tmp);
-    aff_sort_kernel<<<(N + 7) / 8, 256, 0, st>>>(a.start, N, a.src_tmp, a.val_tmp, a.src, a.val);
+    aff_sort_kernel<<<N, 256, 0, st>>>(a.start, N, a.src_tmp, a.val_tmp, a.src, a.val);
     g_sed_launches += 4;
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SED_OK : SED_ERR_CUDA_BASE - (int)e;

@@ -154,24 +154,36 @@ def test_gpu_hpnet_process_builds_spectral_vectors(dev, golden, case, tmp_path, 
     ent = float(torch.load("src/normal_smooth_cache/WUs_5_0.1_50.pt"))
     assert float((torch.norm(v, dim=-1) - 1).abs().max()) < 1e-5
 
-    def close(a, ref, what):
-        ang = _subspace_angles(a, ref)
-        assert float(ang.max()) < 5e-2 and float(_subspace_angles(a[:, :8], ref[:, :8]).max()) < 2e-2, (what, ang)
-        d = (_align_signs(a, ref) - ref).abs()
-        assert float(d.max()) < 5e-2 and float(d.mean()) < 5e-4, (what, float(d.max()), float(d.mean()))
-
+    # the Ritz vectors BEFORE the row normalisation (:192), from the same operator and start block
     op = snm.construction_affinity_matrix_normal(P.to(dev), Nn.to(dev), sigma=0.1, knn=50)
+    E_g, V_g = snm.lobpcg_top(lambda Y: op.matmul(0, Y), n, 12, 10, X0.to(dev))
+    E_g, V_g = E_g.cpu(), V_g.cpu()
+    assert float((v - V_g / (torch.norm(V_g, dim=-1, keepdim=True) + 1e-16)).abs().max()) < 1e-5     # deterministic
     A = op.to_dense()[0].cpu()
     with torch.no_grad():
-        _, V = torch.lobpcg(A, k=12, niter=10, X=X0.clone())
-        v_same = V / (torch.norm(V, dim=-1, keepdim=True) + 1e-16)
+        E_c, V_c = torch.lobpcg(A, k=12, niter=10, X=X0.clone())
+
+    def close(Vg, Vc, what):
+        ang = _subspace_angles(Vg, Vc)
+        assert float(ang.max()) < 5e-2 and float(_subspace_angles(Vg[:, :8], Vc[:, :8]).max()) < 5e-3, (what, ang)
+
+    assert float(((E_g - E_c).abs() / E_c.abs())[:8].max()) < 1e-5 and float(((E_g - E_c).abs() / E_c.abs()).max()) < 2e-3
+    close(V_g, V_c, "torch.lobpcg on the operator's own dense matrix")
+    # after the row normalisation only rows with a real footprint in the 12 vectors are comparable: a point outside their
+    # support has |V_i| ~ 1e-7 |V|_max, and v_i = V_i / |V_i| is then rounding noise of unit length -- in the reference too
+    rn = torch.norm(V_c, dim=-1)
+    strong = rn > 1e-2 * rn.max()
+    v_same = V_c / (rn[:, None] + 1e-16)
+    assert int(strong.sum()) > n // 20
+    assert float((_align_signs(v, v_same) - v_same)[strong].abs().max()) < 5e-2
+    with torch.no_grad():
         ent_same = float(OH.compute_entropy(v_same[None], chunk))
-    close(v, v_same, "torch.lobpcg on the operator's own dense matrix")
-    assert abs(ent - ent_same) < 1e-3
+    assert abs(ent - ent_same) < 3e-2, (ent, ent_same)
     idx_ref = OH.knn_idx(P, 50)[0].numpy()
-    if (np.sort(op.idx[0].cpu().numpy(), 1) == np.sort(idx_ref, 1)).all():
-        close(v, torch.from_numpy(g[f"s{case}_v"]), "recorded reference vectors")
-        assert abs(ent - float(g[f"s{case}_ent"])) < 1e-3
+    if (np.sort(op.idx[0].cpu().numpy(), 1) == np.sort(idx_ref, 1)).all():          # same index table as the recorded run
+        vr = torch.from_numpy(g[f"s{case}_v"])
+        assert float((_align_signs(v, vr) - vr)[strong].abs().max()) < 5e-2
+        assert abs(ent - float(g[f"s{case}_ent"])) < 3e-2
     ref = torch.from_numpy(g[f"s{case}_emb_sample"])
     got = emb[0, ::25].cpu()
     assert float((got[:, :128] - ref[:, :128]).abs().max()) < 1e-4          # features x (1.7 - entropy)
