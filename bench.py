@@ -303,6 +303,9 @@ def kernel_legs(dev, pk):
         row[f"mode{mode}"] = {"ms_per_batch": ms, "clouds_per_s": B / (ms / 1e3),
                               "ms_tflops_algorithmic": B * (2 * ITERS + 3) * 2.0 * NPTS * NPTS * DIM / (ms / 1e3) / 1e12}
     row["segments_recovered"] = bool((nlab.cpu().numpy() == np.array([len(np.unique(l)) for l in lab])).all())
+    # the fit kernel alone on the recovered segments (one CTA per (cloud, segment), each scanning the cloud's labels)
+    row["fit_segments_ms"] = event_ms(lambda: fit_segments_batched(P, Nn, labels, ST), 5)
+    row["fitted_segments"] = int(sum(len(np.unique(l)) for l in lab))
     cfg["configs[3]"] = dict(workload="batch=64 x 10000-pt planted embeddings (12 patches): bandwidth + mean-shift 50 it + nms + "
                                       "fits of every segment (4 primitive types) + residuals", **row)
     return kernels, cfg
