@@ -29,6 +29,11 @@ int pw_gemm(const float* X, long long x_bstride, int ldx, const float* Wt, int l
 int pw_gemm_tc(const float* X, long long x_bstride, int ldx, const float* Wt, int ldw, const float* bias,
                long long bias_bstride, const float* in_a, const float* in_s, int in_act, float* Y, long long y_bstride,
                int ldy, int y_point_major, double* stats, float* mm, int B, int Cin, int Cout, int N, cudaStream_t st);
+// weight-stationary persistent tensor-core implementation (pointwise_tc2.cu); SED_ERR_UNSUPPORTED outside its range
+// (Cin < 32, Cin > 256, Cout < 64)
+int pw_gemm_tc2(const float* X, long long x_bstride, int ldx, const float* Wt, int ldw, const float* bias,
+                long long bias_bstride, const float* in_a, const float* in_s, int in_act, float* Y, long long y_bstride,
+                int ldy, int y_point_major, double* stats, float* mm, int B, int Cin, int Cout, int N, cudaStream_t st);
 int gn_finalize(const double* part, int P, int NBLK, int blocks_per_group, double count, const float* gamma,
                 const float* beta, int B, int C, int G, float eps, float* a_out, float* s_out, cudaStream_t st);
 int edge_fold_weights(const float* W, int Cout, int Cin, float* Wf, cudaStream_t st);

@@ -433,6 +433,13 @@ int pw_gemm(const float* X, long long x_bstride, int ldx, const float* Wt, int l
     if ((in_a == nullptr) != (in_s == nullptr)) return SED_ERR_ARG;
     // SEDNET_B200_PW=ffma forces the CUDA-core kernel of this file (A/B comparisons); default: tensor cores
     static const bool ffma = [] { const char* e = getenv("SEDNET_B200_PW"); return e && !strcmp(e, "ffma"); }();
+    // SEDNET_B200_PW=tc1 keeps every shape on the first tensor-core kernel (one tile per CTA, pointwise_tc.cu)
+    static const bool tc1 = [] { const char* e = getenv("SEDNET_B200_PW"); return e && !strcmp(e, "tc1"); }();
+    if (!ffma && !tc1) {
+        const int rc = pw_gemm_tc2(X, x_bstride, ldx, Wt, ldw, bias, bias_bstride, in_a, in_s, in_act, Y, y_bstride, ldy,
+                                   y_point_major, stats, mm, B, Cin, Cout, N, stream);
+        if (rc != SED_ERR_UNSUPPORTED) return rc;
+    }
     if (!ffma) {
         const int rc = pw_gemm_tc(X, x_bstride, ldx, Wt, ldw, bias, bias_bstride, in_a, in_s, in_act, Y, y_bstride, ldy,
                                   y_point_major, stats, mm, B, Cin, Cout, N, stream);

@@ -332,6 +332,13 @@ __global__ void pw_prep_weights_kernel(const float* __restrict__ W, int ldw, int
     if (lane == 0) rscale[row] = 1.0f / sc;
 }
 
+int pw_prep_weights(const float* W, int ldw, int Cout, int Cin, int cin_pad, __half* Wh, __half* Wl, float* rscale,
+                    cudaStream_t st) {
+    pw_prep_weights_kernel<<<(Cout + 7) / 8, 256, 0, st>>>(W, ldw, Cout, Cin, cin_pad, Wh, Wl, rscale);
+    SED_CHECK_LAUNCH();
+    return SED_OK;
+}
+
 // (rows, width) fp16 row-major weight matrix: box 64 channels x 256 rows, 128B swizzle, rows past the end read as zero
 static int make_map_w(CUtensorMap* m, const __half* base, int rows, int width) {
     EncodeTiledFn fn = get_encode_fn();

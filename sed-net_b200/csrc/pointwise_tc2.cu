@@ -1,0 +1,344 @@
+// 1x1 convolutions of the SEDNet forward, weight-stationary and persistent (tcgen05 + TMEM), sm_100a.
+//
+// Same contract as pw_gemm (pointwise.cu):  Y = W . act(in_a * X + in_s) + bias  over channel-major activations, with the
+// GroupNorm partial statistics and the max / min pooling of the output produced in the epilogue -- reference
+// src/SEDNet.py:78-98 (EdgeConv per-point GEMM, mlp1) and :292-342 (conv1 and the heads).
+//
+// pw_tc_kernel (pointwise_tc.cu) gives every CTA one 128-point x 256-channel tile: per tile it pays a prologue (TMEM
+// allocation, barriers, first loads), streams 64 KB of weights per 64 input channels from L2 and ends in an epilogue that
+// nothing overlaps -- its tensor pipe is 3-19 % busy (profiles/pw_tc_r1.md).  This kernel turns the product around:
+//     D[co, point] (TMEM, FP32) = W[co, c] . X[c, point]
+//   * A = a 128-row tile of the WEIGHTS, loaded ONCE per CTA into tensor memory (FP16 hi | lo of w * 2^k, k per row:
+//     <= 256 of the 512 columns) and kept there while the CTA walks over its share of the 128-point tiles;
+//   * B = activations.  FP32 channel-major in HBM, they need the previous layer's GroupNorm affine + activation: eight
+//     producer warps load them coalesced, transform, split each value into FP16 hi + lo and write the canonical MN-major
+//     128B-swizzle image (points contiguous) into a 4-stage shared-memory ring;
+//   * D += Wh.Xh + Wh.Xl + Wl.Xh (22 significant bits per operand, FP32 accumulation) into one of TWO accumulators, so the
+//     MMA warp works on tile t + 1 while four epilogue warps drain tile t;
+//   * epilogue: thread = output channel (TMEM lane), columns = points: row scale 2^-k, bias, statistics and max / min are
+//     per-thread running values (no shuffles per element), channel-major stores are 128 contiguous bytes per thread.
+// Weights never travel again after the first load; what is re-read (from L2) is the activation tile, once per 128 output
+// channels.
+#include <algorithm>
+
+#include "tc_common.cuh"
+
+namespace sed {
+
+constexpr int P2_THREADS = 448;          // warp 0 TMEM / idle, warp 1 MMA, warps 2-9 producers, warps 10-13 epilogue
+constexpr int P2_M = 128;                // output channels per CTA (UMMA M, TMEM lanes)
+constexpr int P2_N = 128;                // points per tile (UMMA N)
+constexpr int P2_KC = 64;                // input channels per stage
+constexpr int P2_STAGES = 4;
+constexpr int P2_KMAX = 256;             // input channels held in tensor memory (hi + lo: 256 columns)
+constexpr uint32_t P2_PART = P2_N * P2_KC * 2;       // 16 KB: [2 halves of 64 points][64 channels][64 points] fp16
+constexpr uint32_t P2_STAGE = 2 * P2_PART;            // hi + lo
+constexpr uint32_t P2_COL_D = 256;                    // accumulators at columns [256,384) and [384,512)
+
+struct P2Params {
+    const float* X; long long x_bstride; int ldx;
+    const __half* Wh; const __half* Wl;        // (Cout, kpad) pre-split weights
+    const float* rscale;                       // (Cout) 2^-k of the weight rows
+    const float* bias; long long bias_bstride;
+    const float* in_a; const float* in_s; int in_act;
+    float* Y; long long y_bstride; int ldy; int y_point_major;
+    double* stats; float* mm;
+    int Cin, Cout, N, kpad, B, tiles_per_cloud, ctas_per_group;
+};
+
+__device__ __forceinline__ float p2_act(float v, int act) {
+    if (act == 1) return fmaxf(v, 0.f);
+    if (act == 2) return v >= 0.f ? v : 0.2f * v;
+    return v;
+}
+
+__global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(P2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw0 = smem_u32(smem_raw);
+    const uint32_t stage_addr = (raw0 + 1023u) & ~1023u;                    // P2_STAGES x [Xh | Xl]
+    const uint32_t bar_base = stage_addr + P2_STAGES * P2_STAGE;
+    const uint32_t bar_x_full = bar_base;                      // [STAGES] 8 producer warps arrive
+    const uint32_t bar_x_empty = bar_x_full + 8 * P2_STAGES;   // [STAGES] MMA commit
+    const uint32_t bar_d_full = bar_x_empty + 8 * P2_STAGES;   // [2] MMA commit
+    const uint32_t bar_d_empty = bar_d_full + 16;              // [2] 128 epilogue threads
+    const uint32_t bar_w_full = bar_d_empty + 16;              // 128 epilogue threads have written the weights
+    const uint32_t tmem_slot = bar_w_full + 8;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw0));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int co0 = blockIdx.y * P2_M;
+    const int nk = p.kpad / P2_KC;
+    const int total_tiles = p.B * p.tiles_per_cloud;
+    const int G = p.ctas_per_group;
+    const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / G + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P2_STAGES; ++s) { mbar_init(bar_x_full + 8 * s, 8); mbar_init(bar_x_empty + 8 * s, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(bar_d_full + 8 * i, 1); mbar_init(bar_d_empty + 8 * i, 128); }
+        mbar_init(bar_w_full, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 1) {
+        // ============================================================ MMA issuer
+        if (my_tiles > 0 && elect_one()) {
+            constexpr uint32_t IDESC = make_idesc_n(1, P2_N);     // B (activations) MN-major, N = 128
+            const uint32_t w_hi = tmem, w_lo = tmem + (uint32_t)(p.kpad >> 1);
+            mbar_wait(bar_w_full, 0);
+            tc_fence_after();
+            int it = 0;                                            // running chunk counter over all my tiles
+            for (int t = 0; t < my_tiles; ++t) {
+                const int buf = t & 1;
+                if (t >= 2) { mbar_wait(bar_d_empty + 8 * buf, ((t >> 1) - 1) & 1); tc_fence_after(); }
+                const uint32_t d = tmem + P2_COL_D + (uint32_t)buf * P2_N;
+                for (int kc = 0; kc < nk; ++kc, ++it) {
+                    const int s = it % P2_STAGES;
+                    mbar_wait(bar_x_full + 8 * s, (it / P2_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t x_hi = stage_addr + s * P2_STAGE, x_lo = x_hi + P2_PART;
+#pragma unroll
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t wa = ((term == 2) ? w_lo : w_hi) + (uint32_t)kc * (P2_KC / 2);   // Wh, Wh, Wl
+                        const uint32_t xb = (term == 1) ? x_lo : x_hi;                                  // Xh, Xl, Xh
+#pragma unroll
+                        for (int ks = 0; ks < P2_KC / 16; ++ks)
+                            // B: MN-major, 16 channels = 16 rows of 128 B; the two halves of 64 points are P2_PART / 2 apart
+                            umma_ts(d, wa + ks * 8, make_desc(xb + ks * 2048, P2_PART / 2), IDESC,
+                                    (kc > 0 || term > 0 || ks > 0) ? 1u : 0u);
+                    }
+                    tc_commit(bar_x_empty + 8 * s);
+                }
+                tc_commit(bar_d_full + 8 * buf);
+            }
+        }
+    } else if (warp >= 2 && warp < 10) {
+        // ============================================================ producers: activations -> FP16 hi/lo MN-major image
+        const int pw = warp - 2;                                 // 0..7: eight channels of every 64-channel chunk
+        const int chunk = lane & 15;                             // 8 consecutive points
+        const bool x_al = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && ((p.x_bstride & 3) == 0);
+        // raw activations of one K chunk: 4 channel rows x 8 points per thread.  The loads of the next chunk (possibly of
+        // the next tile) are issued before the current one is converted.
+        auto fetch = [&](int t, int kc, float (&r)[4][8]) {
+            const int tile = (int)blockIdx.x + t * G;
+            const int b = tile / p.tiles_per_cloud, n0 = (tile % p.tiles_per_cloud) * P2_N;
+            const float* X = p.X + (long long)b * p.x_bstride;
+            const int pt = n0 + chunk * 8;
+            const bool vec_ok = x_al && (pt + 7 < p.N);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = kc * P2_KC + pw * 8 + q * 2 + (lane >> 4);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r[q][e] = 0.f;
+                if (c < p.Cin) {
+                    const float* src = X + (long long)c * p.ldx + pt;
+                    if (vec_ok) {
+                        const float4 u0 = __ldg(reinterpret_cast<const float4*>(src));
+                        const float4 u1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                        r[q][0] = u0.x; r[q][1] = u0.y; r[q][2] = u0.z; r[q][3] = u0.w;
+                        r[q][4] = u1.x; r[q][5] = u1.y; r[q][6] = u1.z; r[q][7] = u1.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) if (pt + e < p.N) r[q][e] = __ldg(src + e);
+                    }
+                }
+            }
+        };
+        float nxt[4][8];
+        if (my_tiles > 0) fetch(0, 0, nxt);
+        int it = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int tile = (int)blockIdx.x + t * G;
+            const int b = tile / p.tiles_per_cloud, n0 = (tile % p.tiles_per_cloud) * P2_N;
+            const int pt = n0 + chunk * 8;
+            const float* ia = p.in_a ? p.in_a + (long long)b * p.Cin : nullptr;
+            const float* is = p.in_s ? p.in_s + (long long)b * p.Cin : nullptr;
+            for (int kc = 0; kc < nk; ++kc, ++it) {
+                const int s = it % P2_STAGES;
+                float cur[4][8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) cur[q][e] = nxt[q][e];
+                if (kc + 1 < nk) fetch(t, kc + 1, nxt);
+                else if (t + 1 < my_tiles) fetch(t + 1, 0, nxt);
+                if (it >= P2_STAGES) mbar_wait(bar_x_empty + 8 * s, ((it / P2_STAGES) - 1) & 1);
+                const uint32_t x_hi = stage_addr + s * P2_STAGE, x_lo = x_hi + P2_PART;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cl = pw * 8 + q * 2 + (lane >> 4);     // channel within the chunk = row of the image
+                    const int c = kc * P2_KC + cl;
+                    float (&v)[8] = cur[q];
+                    if (c < p.Cin && ia) {
+                        const float av = __ldg(ia + c), sv = __ldg(is + c);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = (pt + e < p.N) ? p2_act(fmaf(av, v[e], sv), p.in_act) : 0.f;
+                    }
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+                        hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+                        lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
+                    // image: [half = point / 64][row = channel][128 B = 64 points], 16-byte chunks XOR-swizzled by (row & 7)
+                    const uint32_t off = (uint32_t)(chunk >> 3) * (P2_PART / 2) + (uint32_t)cl * 128u +
+                                         (uint32_t)(((chunk & 7) ^ (cl & 7)) << 4);
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(x_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(x_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_x_full + 8 * s);
+            }
+        }
+    } else if (warp >= 10) {
+        // ============================================================ epilogue warps: thread = output channel
+        const int quarter = warp & 3;                           // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;
+        const int co = co0 + row;
+        const bool cvalid = co < p.Cout;
+        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        {   // ---- this thread's weight row -> TMEM: hi at columns [0, kpad/2), lo at [kpad/2, kpad)
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {
+                const uint4* g4 = reinterpret_cast<const uint4*>((part ? p.Wl : p.Wh) + (long long)min(co, p.Cout - 1) * p.kpad);
+                const uint32_t wb = tmem + lane_addr + (uint32_t)part * (uint32_t)(p.kpad >> 1);
+#pragma unroll 1
+                for (int c = 0; c < p.kpad / 32; ++c) {          // 32 halves = 16 columns per store
+                    uint32_t w[16];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (cvalid) v = __ldg(g4 + c * 4 + i);
+                        w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+                    }
+                    tmem_st16(wb + c * 16, w);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(bar_w_full);
+        }
+        const float rs = cvalid ? __ldg(p.rscale + co) : 0.f;
+        const int nblk = (p.Cout + 31) / 32;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int tile = (int)blockIdx.x + t * G;
+            const int b = tile / p.tiles_per_cloud, tp = tile % p.tiles_per_cloud, n0 = tp * P2_N;
+            const int buf = t & 1;
+            const float bv = (cvalid && p.bias) ? __ldg(p.bias + (long long)b * p.bias_bstride + co) : 0.f;
+            mbar_wait(bar_d_full + 8 * buf, (t >> 1) & 1);
+            tc_fence_after();
+            const uint32_t db = tmem + lane_addr + P2_COL_D + (uint32_t)buf * P2_N;
+            float s1 = 0.f, s2 = 0.f, mx = -INFINITY, mn = INFINITY;
+            double ds1 = 0.0, ds2 = 0.0;
+#pragma unroll 1
+            for (int cc = 0; cc < 4; ++cc) {
+                uint32_t v[32];
+                tmem_ld32(db + cc * 32, v);
+                tmem_ld_wait();
+                if (cc == 3) {                                  // every tcgen05.ld of this accumulator has completed
+                    tc_fence_before();
+                    mbar_arrive(bar_d_empty + 8 * buf);
+                }
+                const int nb = n0 + cc * 32;
+                float y[32];
+                s1 = 0.f; s2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    y[i] = __fadd_rn(__uint_as_float(v[i]) * rs, bv);
+                    if (nb + i < p.N) {
+                        s1 += y[i]; s2 = fmaf(y[i], y[i], s2);
+                        mx = fmaxf(mx, y[i]); mn = fminf(mn, y[i]);
+                    }
+                }
+                ds1 += (double)s1; ds2 += (double)s2;
+                if (p.Y && cvalid) {
+                    float* Yb = p.Y + (long long)b * p.y_bstride;
+                    if (p.y_point_major) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (nb + i < p.N) Yb[(long long)(nb + i) * p.ldy + co] = y[i];        // lanes = consecutive channels
+                    } else {
+                        float* o = Yb + (long long)co * p.ldy + nb;
+                        if (nb + 31 < p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                reinterpret_cast<float4*>(o)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) if (nb + i < p.N) o[i] = y[i];
+                        }
+                    }
+                }
+            }
+            if (p.stats) {                                      // one 32-channel block per warp: fixed-order butterfly
+                const double t1 = warp_sum_d(cvalid ? ds1 : 0.0), t2 = warp_sum_d(cvalid ? ds2 : 0.0);
+                const int blk = (co0 >> 5) + quarter;
+                if (lane == 0 && blk < nblk) {
+                    double* o = p.stats + (((long long)b * p.tiles_per_cloud + tp) * nblk + blk) * 2;
+                    o[0] = t1; o[1] = t2;
+                }
+            }
+            if (p.mm && cvalid) {
+                float* o = p.mm + (((long long)b * p.tiles_per_cloud + tp) * p.Cout + co) * 2;
+                o[0] = mx; o[1] = mn;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// pointwise_tc.cu: hi / lo FP16 split of w * 2^k (k per row) into rows of cin_pad halves, rscale[row] = 2^-k
+int pw_prep_weights(const float* W, int ldw, int Cout, int Cin, int cin_pad, __half* Wh, __half* Wl, float* rscale,
+                    cudaStream_t st);
+
+// Weight-stationary implementation of pw_gemm (same arguments).  SED_ERR_UNSUPPORTED for shapes it does not cover:
+// Cin < 32 (FFMA kernel), Cin > 256 (the weight tile must fit 256 TMEM columns: pw_tc_kernel), Cout < 64.
+int pw_gemm_tc2(const float* X, long long x_bstride, int ldx, const float* Wt, int ldw, const float* bias,
+                long long bias_bstride, const float* in_a, const float* in_s, int in_act, float* Y, long long y_bstride,
+                int ldy, int y_point_major, double* stats, float* mm, int B, int Cin, int Cout, int N, cudaStream_t st) {
+    if (Cin < 32 || Cin > P2_KMAX || Cout < 64) return SED_ERR_UNSUPPORTED;
+    const int kpad = (Cin + P2_KC - 1) / P2_KC * P2_KC;
+    const size_t wbytes = (size_t)Cout * kpad * sizeof(__half);
+    ensure_pool_config();
+    char* buf = nullptr;
+    SED_CUDA(cudaMallocAsync((void**)&buf, 2 * align_up(wbytes) + (size_t)Cout * sizeof(float), st));
+    __half* Wh = (__half*)buf;
+    __half* Wl = (__half*)(buf + align_up(wbytes));
+    float* rscale = (float*)(buf + 2 * align_up(wbytes));
+    int rc = pw_prep_weights(Wt, ldw, Cout, Cin, kpad, Wh, Wl, rscale, st);
+    const int tiles_per_cloud = (N + P2_N - 1) / P2_N;
+    const int groups = (Cout + P2_M - 1) / P2_M;
+    const int G = std::max(1, std::min(kNumSMs / groups, B * tiles_per_cloud));
+    P2Params p{X, x_bstride, ldx, Wh, Wl, rscale, bias, bias_bstride, in_a, in_s, in_act, Y, y_bstride, ldy, y_point_major,
+               stats, mm, Cin, Cout, N, kpad, B, tiles_per_cloud, G};
+    constexpr size_t smem = (size_t)P2_STAGES * P2_STAGE + 1024 + 256;
+    static_assert(smem <= 227 * 1024, "shared memory budget");
+    cudaError_t e = cudaFuncSetAttribute(pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) rc = SED_ERR_CUDA_BASE - (int)e;
+    if (rc == SED_OK) {
+        pw_tc2_kernel<<<dim3(G, groups), P2_THREADS, smem, st>>>(p);
+        ++g_sed_launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) rc = SED_ERR_CUDA_BASE - (int)e;
+    }
+    cudaFreeAsync(buf, st);
+    return rc;
+}
+
+}  // namespace sed

@@ -459,6 +459,9 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
     return v;
 }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {
+    asm volatile("{ .reg .u16 t; cvt.u16.u32 t, %1; st.shared.u16 [%0], t; }" ::"r"(a), "r"(v));
+}
 // The prune-booking words are shared between warps without a barrier on purpose (a hint that arrives late only moves a
 // prune to a later tile).  They are read and written with shared-memory atomics -- one lane per warp, the value broadcast
 // by a shuffle -- so that concurrent access is well defined (and compute-sanitizer's racecheck has nothing to report).
