@@ -10,9 +10,10 @@
 //     D[co, point] (TMEM, FP32) = W[co, c] . X[c, point]
 //   * A = a 128-row tile of the WEIGHTS, loaded ONCE per CTA into tensor memory (FP16 hi | lo of w * 2^k, k per row:
 //     <= 256 of the 512 columns) and kept there while the CTA walks over its share of the 128-point tiles;
-//   * B = activations.  FP32 channel-major in HBM, they need the previous layer's GroupNorm affine + activation: eight
-//     producer warps load them coalesced, transform, split each value into FP16 hi + lo and write the canonical MN-major
-//     128B-swizzle image (points contiguous) into a 4-stage shared-memory ring;
+//   * B = activations.  FP32 channel-major in HBM, they need the previous layer's GroupNorm affine + activation: TMA stages
+//     the raw 64-channel x 128-point FP32 boxes in a 3-deep ring (96 KB in flight per SM hide the L2 latency that register
+//     prefetching could not), eight producer warps read them, transform, split each value into FP16 hi + lo and write the
+//     canonical MN-major 128B-swizzle image (points contiguous) into a 3-stage operand ring;
 //   * D += Wh.Xh + Wh.Xl + Wl.Xh (22 significant bits per operand, FP32 accumulation) into one of TWO accumulators, so the
 //     MMA warp works on tile t + 1 while four epilogue warps drain tile t;
 //   * epilogue: thread = output channel (TMEM lane), columns = points: row scale 2^-k, bias, statistics and max / min are
@@ -25,14 +26,16 @@
 
 namespace sed {
 
-constexpr int P2_THREADS = 448;          // warp 0 TMEM / idle, warp 1 MMA, warps 2-9 producers, warps 10-13 epilogue
+constexpr int P2_THREADS = 448;          // warp 0 TMEM + TMA (raw activations), warp 1 MMA, warps 2-9 producers, warps 10-13 epilogue
 constexpr int P2_M = 128;                // output channels per CTA (UMMA M, TMEM lanes)
 constexpr int P2_N = 128;                // points per tile (UMMA N)
 constexpr int P2_KC = 64;                // input channels per stage
-constexpr int P2_STAGES = 4;
+constexpr int P2_STAGES = 3;             // FP16 operand stages
+constexpr int P2_RAW = 3;                // raw FP32 stages (TMA)
 constexpr int P2_KMAX = 256;             // input channels held in tensor memory (hi + lo: 256 columns)
 constexpr uint32_t P2_PART = P2_N * P2_KC * 2;       // 16 KB: [2 halves of 64 points][64 channels][64 points] fp16
 constexpr uint32_t P2_STAGE = 2 * P2_PART;            // hi + lo
+constexpr uint32_t P2_RAW_BYTES = P2_N * P2_KC * 4;   // 32 KB: [64 channels][128 points] f32
 constexpr uint32_t P2_COL_D = 256;                    // accumulators at columns [256,384) and [384,512)
 
 struct P2Params {
@@ -52,17 +55,20 @@ __device__ __forceinline__ float p2_act(float v, int act) {
     return v;
 }
 
-__global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(P2Params p) {
+__global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_constant__ CUtensorMap map_x, P2Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw0 = smem_u32(smem_raw);
     const uint32_t stage_addr = (raw0 + 1023u) & ~1023u;                    // P2_STAGES x [Xh | Xl]
-    const uint32_t bar_base = stage_addr + P2_STAGES * P2_STAGE;
+    const uint32_t raw_addr = stage_addr + P2_STAGES * P2_STAGE;            // P2_RAW x [64 channels][128 points] f32
+    const uint32_t bar_base = raw_addr + P2_RAW * P2_RAW_BYTES;
     const uint32_t bar_x_full = bar_base;                      // [STAGES] 8 producer warps arrive
     const uint32_t bar_x_empty = bar_x_full + 8 * P2_STAGES;   // [STAGES] MMA commit
     const uint32_t bar_d_full = bar_x_empty + 8 * P2_STAGES;   // [2] MMA commit
     const uint32_t bar_d_empty = bar_d_full + 16;              // [2] 128 epilogue threads
     const uint32_t bar_w_full = bar_d_empty + 16;              // 128 epilogue threads have written the weights
-    const uint32_t tmem_slot = bar_w_full + 8;
+    const uint32_t bar_r_full = bar_w_full + 8;                // [RAW] TMA bytes
+    const uint32_t bar_r_empty = bar_r_full + 8 * P2_RAW;      // [RAW] 8 producer warps have read the box
+    const uint32_t tmem_slot = bar_r_empty + 8 * P2_RAW;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw0));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -76,6 +82,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(P2Params p) {
         for (int s = 0; s < P2_STAGES; ++s) { mbar_init(bar_x_full + 8 * s, 8); mbar_init(bar_x_empty + 8 * s, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_d_full + 8 * i, 1); mbar_init(bar_d_empty + 8 * i, 128); }
         mbar_init(bar_w_full, 128);
+        for (int s = 0; s < P2_RAW; ++s) { mbar_init(bar_r_full + 8 * s, 1); mbar_init(bar_r_empty + 8 * s, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -87,7 +94,22 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(P2Params p) {
     tc_fence_after();
     const uint32_t tmem = *tmem_slot_ptr;
 
-    if (warp == 1) {
+    if (warp == 0) {
+        // ============================================================ TMA: raw FP32 activation boxes of every (tile, chunk)
+        if (my_tiles > 0 && elect_one()) {
+            int it = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int tile = (int)blockIdx.x + t * G;
+                const int b = tile / p.tiles_per_cloud, n0 = (tile % p.tiles_per_cloud) * P2_N;
+                for (int kc = 0; kc < nk; ++kc, ++it) {
+                    const int rs = it % P2_RAW;
+                    if (it >= P2_RAW) mbar_wait(bar_r_empty + 8 * rs, ((it / P2_RAW) - 1) & 1);
+                    mbar_expect_tx(bar_r_full + 8 * rs, P2_RAW_BYTES);
+                    tma_load_3d(raw_addr + rs * P2_RAW_BYTES, &map_x, bar_r_full + 8 * rs, n0, kc * P2_KC, b);   // OOB reads as 0
+                }
+            }
+        }
+    } else if (warp == 1) {
         // ============================================================ MMA issuer
         if (my_tiles > 0 && elect_one()) {
             constexpr uint32_t IDESC = make_idesc_n(1, P2_N);     // B (activations) MN-major, N = 128
@@ -123,36 +145,6 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(P2Params p) {
         // ============================================================ producers: activations -> FP16 hi/lo MN-major image
         const int pw = warp - 2;                                 // 0..7: eight channels of every 64-channel chunk
         const int chunk = lane & 15;                             // 8 consecutive points
-        const bool x_al = ((p.ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) && ((p.x_bstride & 3) == 0);
-        // raw activations of one K chunk: 4 channel rows x 8 points per thread.  The loads of the next chunk (possibly of
-        // the next tile) are issued before the current one is converted.
-        auto fetch = [&](int t, int kc, float (&r)[4][8]) {
-            const int tile = (int)blockIdx.x + t * G;
-            const int b = tile / p.tiles_per_cloud, n0 = (tile % p.tiles_per_cloud) * P2_N;
-            const float* X = p.X + (long long)b * p.x_bstride;
-            const int pt = n0 + chunk * 8;
-            const bool vec_ok = x_al && (pt + 7 < p.N);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int c = kc * P2_KC + pw * 8 + q * 2 + (lane >> 4);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) r[q][e] = 0.f;
-                if (c < p.Cin) {
-                    const float* src = X + (long long)c * p.ldx + pt;
-                    if (vec_ok) {
-                        const float4 u0 = __ldg(reinterpret_cast<const float4*>(src));
-                        const float4 u1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                        r[q][0] = u0.x; r[q][1] = u0.y; r[q][2] = u0.z; r[q][3] = u0.w;
-                        r[q][4] = u1.x; r[q][5] = u1.y; r[q][6] = u1.z; r[q][7] = u1.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; ++e) if (pt + e < p.N) r[q][e] = __ldg(src + e);
-                    }
-                }
-            }
-        };
-        float nxt[4][8];
-        if (my_tiles > 0) fetch(0, 0, nxt);
         int it = 0;
         for (int t = 0; t < my_tiles; ++t) {
             const int tile = (int)blockIdx.x + t * G;
@@ -161,14 +153,16 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(P2Params p) {
             const float* ia = p.in_a ? p.in_a + (long long)b * p.Cin : nullptr;
             const float* is = p.in_s ? p.in_s + (long long)b * p.Cin : nullptr;
             for (int kc = 0; kc < nk; ++kc, ++it) {
-                const int s = it % P2_STAGES;
+                const int s = it % P2_STAGES, rs = it % P2_RAW;
+                // this thread's 4 channel rows x 8 points of the raw box ([channel][128 points] f32, 512-B rows)
                 float cur[4][8];
+                mbar_wait(bar_r_full + 8 * rs, (it / P2_RAW) & 1);
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) cur[q][e] = nxt[q][e];
-                if (kc + 1 < nk) fetch(t, kc + 1, nxt);
-                else if (t + 1 < my_tiles) fetch(t + 1, 0, nxt);
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t ra = raw_addr + rs * P2_RAW_BYTES + (uint32_t)(pw * 8 + q * 2 + (lane >> 4)) * 512u + (uint32_t)chunk * 32u;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][0]), "=f"(cur[q][1]), "=f"(cur[q][2]), "=f"(cur[q][3]) : "r"(ra));
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][4]), "=f"(cur[q][5]), "=f"(cur[q][6]), "=f"(cur[q][7]) : "r"(ra + 16u));
+                }
                 if (it >= P2_STAGES) mbar_wait(bar_x_empty + 8 * s, ((it / P2_STAGES) - 1) & 1);
                 const uint32_t x_hi = stage_addr + s * P2_STAGE, x_lo = x_hi + P2_PART;
 #pragma unroll
@@ -176,7 +170,10 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(P2Params p) {
                     const int cl = pw * 8 + q * 2 + (lane >> 4);     // channel within the chunk = row of the image
                     const int c = kc * P2_KC + cl;
                     float (&v)[8] = cur[q];
-                    if (c < p.Cin && ia) {
+                    if (c >= p.Cin) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                    } else if (ia) {
                         const float av = __ldg(ia + c), sv = __ldg(is + c);
 #pragma unroll
                         for (int e = 0; e < 8; ++e) v[e] = (pt + e < p.N) ? p2_act(fmaf(av, v[e], sv), p.in_act) : 0.f;
@@ -196,9 +193,10 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(P2Params p) {
                     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(x_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
                     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(x_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+                // generic-proxy writes of the image -> tensor-core reads; generic-proxy reads of the raw box -> TMA's next write
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_x_full + 8 * s);
+                if (lane == 0) { mbar_arrive(bar_x_full + 8 * s); mbar_arrive(bar_r_empty + 8 * rs); }
             }
         }
     } else if (warp >= 10) {
@@ -313,6 +311,8 @@ int pw_gemm_tc2(const float* X, long long x_bstride, int ldx, const float* Wt, i
                 long long bias_bstride, const float* in_a, const float* in_s, int in_act, float* Y, long long y_bstride,
                 int ldy, int y_point_major, double* stats, float* mm, int B, int Cin, int Cout, int N, cudaStream_t st) {
     if (Cin < 32 || Cin > P2_KMAX || Cout < 64) return SED_ERR_UNSUPPORTED;
+    // TMA needs 16-byte aligned rows
+    if ((ldx & 3) || (x_bstride & 3) || (reinterpret_cast<uintptr_t>(X) & 15)) return SED_ERR_UNSUPPORTED;
     const int kpad = (Cin + P2_KC - 1) / P2_KC * P2_KC;
     const size_t wbytes = (size_t)Cout * kpad * sizeof(__half);
     ensure_pool_config();
@@ -325,14 +325,26 @@ int pw_gemm_tc2(const float* X, long long x_bstride, int ldx, const float* Wt, i
     const int tiles_per_cloud = (N + P2_N - 1) / P2_N;
     const int groups = (Cout + P2_M - 1) / P2_M;
     const int G = std::max(1, std::min(kNumSMs / groups, B * tiles_per_cloud));
+    // raw activations by TMA: (N, Cin, B) f32 with strides (ldx, x_bstride) elements; box 128 points x 64 channels
+    CUtensorMap mx;
+    if (rc == SED_OK) {
+        EncodeTiledFn fn = get_encode_fn();
+        const cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)Cin, (cuuint64_t)B};
+        const cuuint64_t strides[2] = {(cuuint64_t)ldx * 4, (cuuint64_t)x_bstride * 4};
+        const cuuint32_t box[3] = {P2_N, P2_KC, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        if (!fn || fn(&mx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)X, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            rc = SED_ERR_UNSUPPORTED;
+    }
     P2Params p{X, x_bstride, ldx, Wh, Wl, rscale, bias, bias_bstride, in_a, in_s, in_act, Y, y_bstride, ldy, y_point_major,
                stats, mm, Cin, Cout, N, kpad, B, tiles_per_cloud, G};
-    constexpr size_t smem = (size_t)P2_STAGES * P2_STAGE + 1024 + 256;
+    constexpr size_t smem = (size_t)P2_STAGES * P2_STAGE + (size_t)P2_RAW * P2_RAW_BYTES + 1024 + 256;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     cudaError_t e = cudaFuncSetAttribute(pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) rc = SED_ERR_CUDA_BASE - (int)e;
     if (rc == SED_OK) {
-        pw_tc2_kernel<<<dim3(G, groups), P2_THREADS, smem, st>>>(p);
+        pw_tc2_kernel<<<dim3(G, groups), P2_THREADS, smem, st>>>(mx, p);
         ++g_sed_launches;
         e = cudaGetLastError();
         if (e != cudaSuccess) rc = SED_ERR_CUDA_BASE - (int)e;
