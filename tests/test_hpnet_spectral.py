@@ -170,7 +170,7 @@ def test_gpu_hpnet_process_builds_spectral_vectors(dev, golden, case, tmp_path, 
         ang = _subspace_angles(Vg, Vc)
         assert float(ang.max()) < 5e-2 and float(_subspace_angles(Vg[:, :8], Vc[:, :8]).max()) < 5e-3, (what, ang)
 
-    assert float(((E_g - E_c).abs() / E_c.abs())[:8].max()) < 1e-5 and float(((E_g - E_c).abs() / E_c.abs()).max()) < 2e-3
+    assert float(((E_g - E_c).abs() / E_c.abs())[:8].max()) < 1e-4 and float(((E_g - E_c).abs() / E_c.abs()).max()) < 2e-3
     close(V_g, V_c, "torch.lobpcg on the operator's own dense matrix")
     # after the row normalisation only rows with a real footprint in the 12 vectors are comparable: a point outside their
     # support has |V_i| ~ 1e-7 |V|_max, and v_i = V_i / |V_i| is then rounding noise of unit length -- in the reference too
