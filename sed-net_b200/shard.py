@@ -17,12 +17,29 @@ def shard_range(total, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+MAX_LABELS = 512    # upper bound of a label value (the nms keeps at most 512 centres)
+
+
+def canonical_labels(labels):
+    """(B,N) int64 labels -> the same partitions numbered by first occurrence (device ops, no host sync).  Which of several
+    numerically identical converged points becomes a centre -- and with it the numbering -- may change with the batch a cloud
+    is processed in (the mean-shift kernel's CTA decomposition depends on the batch); the partition does not."""
+    B, N = labels.shape
+    pos = torch.arange(N, device=labels.device).expand(B, N)
+    first = torch.full((B, MAX_LABELS), N, dtype=torch.int64, device=labels.device).scatter_reduce(1, labels, pos, "amin")
+    rank = first.argsort(dim=1, stable=True).argsort(dim=1, stable=True)
+    return rank.gather(1, labels)
+
+
 def make_records(shape_ids, n_labels, status, residual, bw, labels):
-    """(B, len(RECORD_FIELDS)) float64 records from the pipeline outputs of the local shard (tensors on one device)."""
+    """(B, len(RECORD_FIELDS)) float64 records from the pipeline outputs of the local shard (tensors on one device);
+    label_checksum is a position-weighted sum of the canonically numbered labels (equal partitions <=> equal checksums,
+    up to collisions)."""
     fitted = (status != 1)
     nf = fitted.sum(1)
     mean_res = (residual * fitted).sum(1) / nf.clamp(min=1)
-    chk = (labels.to(torch.float64) * (torch.arange(labels.shape[1], device=labels.device, dtype=torch.float64) % 97 + 1)).sum(1)
+    lab = canonical_labels(labels)
+    chk = (lab.to(torch.float64) * (torch.arange(labels.shape[1], device=labels.device, dtype=torch.float64) % 97 + 1)).sum(1)
     cols = [shape_ids, n_labels, nf, mean_res, bw, chk]
     return torch.stack([c.to(torch.float64) for c in cols], 1)
 

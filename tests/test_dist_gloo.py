@@ -46,3 +46,22 @@ def test_two_rank_gather_over_gloo():
     assert (a == b).all()                       # every rank ends with the same table
     assert a[:, 0].tolist() == list(range(total))
     assert abs(a[:3, 4] - 0.1).max() < 1e-6 and abs(a[3:, 4] - 0.2).max() < 1e-6   # rank 0 owns 3 shapes, rank 1 owns 2
+
+
+def test_record_checksum_is_numbering_invariant():
+    """The per-shape label checksum of the gathered records compares PARTITIONS: relabelling a cloud's segments (which of
+    several identical converged points becomes a centre may change with the batch composition) leaves it unchanged, moving a
+    point to another segment changes it."""
+    import numpy as np
+    import oracle as O
+    g = torch.Generator().manual_seed(1)
+    labels = torch.randint(0, 7, (3, 400), generator=g)
+    c = shard.canonical_labels(labels)
+    for b in range(3):
+        assert (c[b].numpy() == O.canonical_labels(labels[b].numpy())).all()
+    perm = torch.tensor([4, 2, 6, 0, 1, 5, 3])
+    args = lambda L: (torch.arange(3), torch.full((3,), 7), torch.zeros((3, 7), dtype=torch.int32), torch.zeros((3, 7)), torch.ones(3), L)
+    r0, r1 = shard.make_records(*args(labels)), shard.make_records(*args(perm[labels]))
+    assert torch.equal(r0, r1)
+    moved = labels.clone(); moved[1, 17] = (moved[1, 17] + 1) % 7
+    assert not torch.equal(shard.make_records(*args(moved))[:, 5], r0[:, 5])
