@@ -284,6 +284,15 @@ int sed_type_vote_weighted(const int64_t* types, const float* weights, int N, in
  * the reference's operation order); the caller averages ((mean min_a + mean min_b) / 2). */
 int sed_chamfer_min(const float* a, const float* b, int B, int n, int m, float* min_a, float* min_b, sed_stream_t stream);
 
+/* The reference's chamfer extension, src/chamfer_distance/chamfer_distance.cu:6-158 (forward_cuda) and :161-187
+ * (backward_cuda), bound by src/chamfer_distance/chamfer_distance.py:44-75: xyz1 (B,n,3), xyz2 (B,m,3) ->
+ * dist1 (B,n) / idx1 (B,n) int32 = squared distance to / index of the nearest point of xyz2 (lowest index on ties), dist2 /
+ * idx2 (B,m) the other way round; backward: grad_xyz1 (B,n,3), grad_xyz2 (B,m,3) from grad_dist1 / grad_dist2 (zeroed here). */
+int sed_chamfer_forward(const float* xyz1, const float* xyz2, int B, int n, int m, float* dist1, float* dist2, int* idx1,
+                        int* idx2, sed_stream_t stream);
+int sed_chamfer_backward(const float* xyz1, const float* xyz2, const float* grad_dist1, const float* grad_dist2, const int* idx1,
+                         const int* idx2, int B, int n, int m, float* grad_xyz1, float* grad_xyz2, sed_stream_t stream);
+
 /* The chamfer terms of ALL matched segment pairs of mean_IOU_primitive_segment_usecd (src/segment_utils.py:473) in one
  * pass: pred2gt, gt2pred (B,K) int32 matched partner of every segment or -1.  min_pred (B,N)[i] = distance^2 from point
  * i to the nearest point of the gt segment matched to i's predicted segment; min_gt (B,N)[i] = to the nearest point of

@@ -51,6 +51,8 @@ SIGNATURES = {
                                c_vp]),
     "sed_type_vote_weighted": (I, [c_i64p, c_f32p, I, I, I, c_f32p, c_vp]),
     "sed_chamfer_min": (I, [c_f32p, c_f32p, I, I, I, c_f32p, c_f32p, c_vp]),
+    "sed_chamfer_forward": (I, [c_f32p, c_f32p, I, I, I, c_f32p, c_f32p, c_i32p, c_i32p, c_vp]),
+    "sed_chamfer_backward": (I, [c_f32p, c_f32p, c_f32p, c_f32p, c_i32p, c_i32p, I, I, I, c_f32p, c_f32p, c_vp]),
     "sed_matched_chamfer": (I, [c_f32p, c_i64p, c_i64p, c_i32p, c_i32p, I, I, I, c_f32p, c_f32p, c_vp]),
     "sed_lstsq3": (I, [c_f32p, c_f32p, I, c_f32p, c_i32p, c_vp]),
     "sed_svd3": (I, [c_f32p, I, c_f32p, c_f32p, c_vp]),
