@@ -59,7 +59,8 @@ __global__ void pack_input_kernel(const float* __restrict__ pts, const float* __
 using namespace sed;
 
 struct sed_pipeline {
-    int max_B, N, k, S, E, NP, d;
+    int max_B, N, k, S, E, NP, d;   // d: width of the rows of X for the clustering half (128 = the network's embedding)
+    int dmax;                       // allocated width of X / shifted / centres (192: room for the 148-column hpnet embedding)
     // weights
     float* wbuf[2];
     const float* wptr[2][SED_P_COUNT];
@@ -130,8 +131,8 @@ int sed_pipeline_create(int max_B, int N, int k, int max_segments, sed_pipeline_
     sed_pipeline* p = new (std::nothrow) sed_pipeline();
     if (!p) return SED_ERR_ARG;
     memset(p, 0, sizeof(*p));
-    p->max_B = max_B; p->N = N; p->k = k; p->S = max_segments; p->E = 128; p->NP = 6; p->d = 128;
-    const size_t B = max_B, n = N, S = max_segments, d = p->d;
+    p->max_B = max_B; p->N = N; p->k = k; p->S = max_segments; p->E = 128; p->NP = 6; p->d = 128; p->dmax = 192;
+    const size_t B = max_B, n = N, S = max_segments, d = p->dmax;
     int64_t wtot = 0;
     for (int i = 0; i < SED_P_COUNT; ++i) wtot += align_up(param_numel(i, p->E, p->NP) * 4);
     p->fwd_ws_bytes = sed_sednet_workspace_bytes(max_B, N, k);
@@ -223,6 +224,7 @@ int sed_pipeline_run_forward(sed_pipeline_t* p, const float* points_dev, const f
     SED_CUDA(cudaEventRecord(p->ev_join, p->side));
     SED_TRY(sed_sednet_forward_g1(p->wptr[1], p->inp, p->idx1, B, N, p->k, 1.0f, 0.2f, p->E, p->NP, p->emb, p->logp,
                                   p->edges, nullptr, nullptr, p->fwd_ws, p->fwd_ws_bytes, st));
+    p->d = p->E;                               // X = the network's own embedding again
     SED_TRY(sed_normalize_transpose(p->emb, B, p->E, N, p->X, st));
     SED_CUDA(cudaStreamWaitEvent(st, p->ev_join, 0));
     SED_CUDA(cudaEventRecord(p->ev[2], st));
@@ -265,6 +267,12 @@ int sed_pipeline_run_cluster(sed_pipeline_t* p, const float* points_dev, const f
     SED_TRY(sed_residual_segments(points_dev, (const int64_t*)p->labels, p->seg_type, p->params, p->status, B, N, S, 1,
                                   p->residual, st));
     SED_CUDA(cudaEventRecord(p->ev[6], st));
+    return SED_OK;
+}
+
+int sed_pipeline_set_cluster_width(sed_pipeline_t* p, int d) {
+    if (!p || d <= 0 || d > p->dmax || (d & 3)) return SED_ERR_ARG;
+    p->d = d;
     return SED_OK;
 }
 

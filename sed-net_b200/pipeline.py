@@ -87,9 +87,25 @@ class Pipeline:
         B = points.shape[0]
         assert points.shape == (B, self.N, 3) and B <= self.B
         _lib.call("sed_pipeline_run_forward", self._h, _lib.ptr(points), _lib.ptr(normals), B, _lib.stream())
+        self._d = 128
 
-    def run_cluster(self, points, normals, quantile=0.015, iterations=50, prec_mode=1):
-        """Second half: guarded mean-shift of the handle's X, type vote, fits, residuals (results on the device)."""
+    def set_cluster_embedding(self, X):
+        """Replace the embedding the clustering half reads: X (B,N,d) float32 CUDA, unit rows, d a multiple of 4 up to 192 (the
+        reference's hpnet_process concatenation is 148 wide, generate_predictions_aug.py:371-380).  run_forward resets the
+        handle to the network's own 128-wide embedding."""
+        X = _lib.require_cuda(X, name="X")
+        B, N, d = X.shape
+        assert N == self.N and B <= self.B
+        _lib.call("sed_pipeline_set_cluster_width", self._h, int(d))
+        self._d = int(d)
+        self.device_tensor_view("X", width=d)[:B].copy_(X)
+
+    def run_cluster(self, points, normals, quantile=0.015, iterations=50, prec_mode=None):
+        """Second half: guarded mean-shift of the handle's X, type vote, fits, residuals (results on the device).
+        prec_mode None = 1 for rows up to 128 wide, 3 for wider ones (the tensor-core kernel of 129..192 columns; mode 1
+        would take the FP32 FFMA kernel there, ~30x slower)."""
+        if prec_mode is None:
+            prec_mode = 1 if getattr(self, "_d", 128) <= 128 else 3
         points = _lib.require_cuda(points, name="points")
         normals = _lib.require_cuda(normals, name="normals")
         B = points.shape[0]
@@ -111,10 +127,11 @@ class Pipeline:
                    X=("BNd", torch.float32), shifted=("BNd", torch.float32), embedding=("BdN", torch.float32),
                    log_prob=("B6N", torch.float32), type_log_prob=("B6N", torch.float32))
 
-    def device_tensor_view(self, name):
-        """Zero-copy torch view of a named device buffer of the handle (valid for the handle's lifetime)."""
+    def device_tensor_view(self, name, width=None):
+        """Zero-copy torch view of a named device buffer of the handle (valid for the handle's lifetime).  X / shifted are
+        dense (B,N,d) at the current clustering width (128 unless set_cluster_embedding changed it; `width` overrides)."""
         code, dt = self._SHAPES[name]
-        dims = dict(B=self.B, N=self.N, S=self.S, d=128)
+        dims = dict(B=self.B, N=self.N, S=self.S, d=width or getattr(self, "_d", 128))
         shape = tuple(dims[c] if c in dims else int(c) for c in code)
         p = _lib.load().sed_pipeline_device_ptr(self._h, name.encode())
         if not p:

@@ -67,6 +67,7 @@ SIGNATURES = {
     "sed_pipeline_run_device": (I, [c_vp, c_f32p, c_f32p, I, D, I, I, c_vp]),
     "sed_pipeline_run_forward": (I, [c_vp, c_f32p, c_f32p, I, c_vp]),
     "sed_pipeline_run_cluster": (I, [c_vp, c_f32p, c_f32p, I, D, I, I, c_vp]),
+    "sed_pipeline_set_cluster_width": (I, [c_vp, I]),
     "sed_pipeline_device_ptr": (c_vp, [c_vp, C.c_char_p]),
     "sed_pipeline_stage_ms": (I, [c_vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "sed_launch_count": (L, [I]),

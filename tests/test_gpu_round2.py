@@ -275,3 +275,50 @@ def test_two_rank_nccl_sharded_equals_single_rank(dev, tmp_path):
     assert torch.equal(gathered[:, :3], single[:, :3])                      # shape id, n_labels, n_fitted
     assert torch.equal(gathered[:, 5], single[:, 5])                        # label checksum: identical segmentation
     assert float((gathered[:, 3:5] - single[:, 3:5]).abs().max()) < 1e-6    # mean residual, bandwidth
+
+
+# ------------------------------------------------------------------------------------------------ driver default: HPNet_embed
+def test_pipeline_clusters_the_148_column_hpnet_embedding(dev):
+    """The driver's default flow (HPNet_embed = True, generate_predictions_aug.py:371-387) through the batched C-ABI step:
+    run_forward -> hpnet_process per shape on the handle's outputs (spectral vectors built on the spot) -> the 148-column
+    embedding goes back into the handle (set_cluster_embedding) -> run_cluster.  Labels, bandwidth and label counts against
+    the oracle chain (oracle hpnet + guarded mean-shift) on the same embedding."""
+    import oracle_hpnet as OH
+    from sednet_b200.pipeline import Pipeline
+    from sednet_b200.src import smooth_normal_matrix as snm
+    B, N, k, it, chunk = 2, 2400, 32, 20, 480
+    pts, nrm, lab, typ = synth.make_batch(B, N, seed0=91, n_patches=6)
+    pipe = Pipeline(B, N, k, max_segments=64)
+    pipe.set_weights(synth.make_state_dict(0), synth.make_state_dict(1, randomize_gn=True))
+    P, Nn = t(pts).to(dev), t(nrm).to(dev)
+    pipe.run_forward(P, Nn)
+    logp = pipe.device_tensor("type_log_prob")           # (B,6,N)
+    embs, refs = [], []
+    for b in range(B):
+        feat = t(synth.make_embedding(lab[b], 128, 0.05, 50 + b))[None] * 3.0      # planted instance features (not unit)
+        g = torch.Generator().manual_seed(b)
+        edges = torch.randn((1, N, 2), generator=g)
+        X0 = torch.randn((1, N, 12), generator=g)
+        types = logp[b].T[None].contiguous()
+        e = snm.hpnet_process(feat.to(dev), P[b:b + 1], Nn[b:b + 1], types=types, edges=edges.to(dev), CHUNK=chunk, X=X0)
+        embs.append(torch.nn.functional.normalize(e[0], p=2, dim=1))
+        with torch.no_grad():
+            v, _ = OH.spectral_vectors(t(pts[b])[None], t(nrm[b])[None], X0)
+            eo = OH.hpnet_combine(feat, v, OH.compute_entropy(v, chunk), types.cpu(), edges, 0.5, chunk)
+            refs.append(O.guard_mean_shift(torch.nn.functional.normalize(eo[0], p=2, dim=1), 0.015, it))
+    X = torch.stack(embs).contiguous()
+    assert X.shape == (B, N, 148)
+    pipe.set_cluster_embedding(X)
+    pipe.run_cluster(P, Nn, 0.015, it)
+    labels = pipe.device_tensor("labels").cpu().numpy()
+    assert pipe.device_tensor_view("shifted").shape == (B, N, 148)
+    for b in range(B):
+        _, rbw, rlab = refs[b]
+        assert (canon(labels[b]) == canon(rlab.numpy())).all(), b
+        assert abs(float(pipe.device_tensor("bw")[b]) - float(rbw)) < 1e-3 * float(rbw)
+        assert int(pipe.device_tensor("n_labels")[b]) == len(np.unique(rlab.numpy()))
+    # a new run_forward puts the handle back on the network's own 128-wide embedding
+    pipe.run_forward(P, Nn)
+    assert pipe.device_tensor_view("X").shape == (B, N, 128)
+    pipe.run_cluster(P, Nn, 0.015, it)
+    pipe.close()
