@@ -371,7 +371,8 @@ int sed_pipeline_run_cluster(sed_pipeline_t* p, const float* points_dev, const f
 /* Width of the rows the clustering half reads from the handle's X buffer, (B,N,d) dense: 128 after run_forward (the network's
  * embedding); a driver that replaced X by a wider embedding -- the reference's hpnet_process concatenation is 148 columns,
  * generate_predictions_aug.py:371-380 -- sets it before run_cluster.  d a multiple of 4, <= 192 (the buffers' allocated width).
- * run_forward resets it to 128. */
+ * run_forward resets it to 128.  Above 128 columns pass prec_mode 3 to run_cluster (the 192-wide tensor-core kernel); mode 1
+ * runs the FP32 FFMA kernel there (see sed_ms_shift). */
 int sed_pipeline_set_cluster_width(sed_pipeline_t* p, int d);
 void* sed_pipeline_device_ptr(sed_pipeline_t* p, const char* name);
 /* device time (ms, CUDA events on the run's stream) of the stages of the last run: first-layer graph (shared by the
