@@ -55,6 +55,50 @@ __device__ __forceinline__ float p2_act(float v, int act) {
     return v;
 }
 
+// FP16 hi / lo split of 8 consecutive points of one channel row and its two 16-byte stores into the operand image
+__device__ __forceinline__ void p2_split_store(const float (&v)[8], uint32_t hi_addr, uint32_t lo_addr) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+        const float2 hf = __half22float2(h);
+        const __half2 l = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
+        hi[e] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
+}
+
+// Interior boxes (all 128 points and all 64 channels exist -- every box but those of a cloud's last tile): no bounds tests,
+// the activation known at compile time, the four rows' scale / shift loaded up front.  ACT: -1 raw (no affine), 0 affine only,
+// 1 affine + ReLU, 2 affine + LeakyReLU(0.2).
+template <int ACT>
+__device__ __forceinline__ void p2_convert_interior(float (&cur)[4][8], const float* __restrict__ ia, const float* __restrict__ is,
+                                                    int c_first, int cl_first, int chunk, uint32_t x_hi, uint32_t x_lo) {
+    float av[4], sv[4];
+    if (ACT >= 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { av[q] = __ldg(ia + c_first + q * 2); sv[q] = __ldg(is + c_first + q * 2); }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int cl = cl_first + q * 2;
+        float (&v)[8] = cur[q];
+        if (ACT >= 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float t = fmaf(av[q], v[e], sv[q]);
+                if (ACT == 1) t = fmaxf(t, 0.f);
+                if (ACT == 2) t = t >= 0.f ? t : 0.2f * t;
+                v[e] = t;
+            }
+        }
+        const uint32_t off = (uint32_t)(chunk >> 3) * (P2_PART / 2) + (uint32_t)cl * 128u + (uint32_t)(((chunk & 7) ^ (cl & 7)) << 4);
+        p2_split_store(v, x_hi + off, x_lo + off);
+    }
+}
+
 __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_constant__ CUtensorMap map_x, P2Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw0 = smem_u32(smem_raw);
@@ -165,33 +209,32 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
                 }
                 if (it >= P2_STAGES) mbar_wait(bar_x_empty + 8 * s, ((it / P2_STAGES) - 1) & 1);
                 const uint32_t x_hi = stage_addr + s * P2_STAGE, x_lo = x_hi + P2_PART;
+                const int cl0 = pw * 8 + (lane >> 4);                                   // this thread's first row of the box
+                if (n0 + P2_N <= p.N && kc * P2_KC + P2_KC <= p.Cin) {                   // interior box (CTA-uniform)
+                    const int c0 = kc * P2_KC + cl0;
+                    if (!ia) p2_convert_interior<-1>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
+                    else if (p.in_act == 1) p2_convert_interior<1>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
+                    else if (p.in_act == 2) p2_convert_interior<2>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
+                    else p2_convert_interior<0>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
+                } else {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int cl = pw * 8 + q * 2 + (lane >> 4);     // channel within the chunk = row of the image
-                    const int c = kc * P2_KC + cl;
-                    float (&v)[8] = cur[q];
-                    if (c >= p.Cin) {
+                    for (int q = 0; q < 4; ++q) {
+                        const int cl = cl0 + q * 2;                  // channel within the chunk = row of the image
+                        const int c = kc * P2_KC + cl;
+                        float (&v)[8] = cur[q];
+                        if (c >= p.Cin) {
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                    } else if (ia) {
-                        const float av = __ldg(ia + c), sv = __ldg(is + c);
+                            for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                        } else if (ia) {
+                            const float av = __ldg(ia + c), sv = __ldg(is + c);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = (pt + e < p.N) ? p2_act(fmaf(av, v[e], sv), p.in_act) : 0.f;
+                            for (int e = 0; e < 8; ++e) v[e] = (pt + e < p.N) ? p2_act(fmaf(av, v[e], sv), p.in_act) : 0.f;
+                        }
+                        // image: [half = point / 64][row = channel][128 B = 64 points], 16-byte chunks XOR-swizzled by (row & 7)
+                        const uint32_t off = (uint32_t)(chunk >> 3) * (P2_PART / 2) + (uint32_t)cl * 128u +
+                                             (uint32_t)(((chunk & 7) ^ (cl & 7)) << 4);
+                        p2_split_store(v, x_hi + off, x_lo + off);
                     }
-                    uint32_t hi[4], lo[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
-                        const float2 hf = __half22float2(h);
-                        const __half2 l = __floats2half2_rn(v[2 * e] - hf.x, v[2 * e + 1] - hf.y);
-                        hi[e] = *reinterpret_cast<const uint32_t*>(&h);
-                        lo[e] = *reinterpret_cast<const uint32_t*>(&l);
-                    }
-                    // image: [half = point / 64][row = channel][128 B = 64 points], 16-byte chunks XOR-swizzled by (row & 7)
-                    const uint32_t off = (uint32_t)(chunk >> 3) * (P2_PART / 2) + (uint32_t)cl * 128u +
-                                         (uint32_t)(((chunk & 7) ^ (cl & 7)) << 4);
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(x_hi + off), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(x_lo + off), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
                 }
                 // generic-proxy writes of the image -> tensor-core reads; generic-proxy reads of the raw box -> TMA's next write
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -252,20 +295,35 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
                 float y[32];
                 s1 = 0.f; s2 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    y[i] = __fadd_rn(__uint_as_float(v[i]) * rs, bv);
-                    if (nb + i < p.N) {
+                for (int i = 0; i < 32; ++i) y[i] = __fadd_rn(__uint_as_float(v[i]) * rs, bv);
+                if (nb + 32 <= p.N) {                           // interior chunk: no per-point tests
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
                         s1 += y[i]; s2 = fmaf(y[i], y[i], s2);
                         mx = fmaxf(mx, y[i]); mn = fminf(mn, y[i]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (nb + i < p.N) {
+                            s1 += y[i]; s2 = fmaf(y[i], y[i], s2);
+                            mx = fmaxf(mx, y[i]); mn = fminf(mn, y[i]);
+                        }
                     }
                 }
                 ds1 += (double)s1; ds2 += (double)s2;
                 if (p.Y && cvalid) {
                     float* Yb = p.Y + (long long)b * p.y_bstride;
                     if (p.y_point_major) {
+                        float* o = Yb + (long long)nb * p.ldy + co;                                 // lanes = consecutive channels
+                        if (nb + 32 <= p.N) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (nb + i < p.N) Yb[(long long)(nb + i) * p.ldy + co] = y[i];        // lanes = consecutive channels
+                            for (int i = 0; i < 32; ++i) o[(long long)i * p.ldy] = y[i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (nb + i < p.N) o[(long long)i * p.ldy] = y[i];
+                        }
                     } else {
                         float* o = Yb + (long long)co * p.ldy + nb;
                         if (nb + 31 < p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
