@@ -71,18 +71,18 @@ __device__ __forceinline__ void p2_split_store(const float (&v)[8], uint32_t hi_
 }
 
 // Interior boxes (all 128 points and all 64 channels exist -- every box but those of a cloud's last tile): no bounds tests,
-// the activation known at compile time, the four rows' scale / shift loaded up front.  ACT: -1 raw (no affine), 0 affine only,
+// the activation known at compile time, the eight rows' scale / shift loaded up front.  ACT: -1 raw (no affine), 0 affine only,
 // 1 affine + ReLU, 2 affine + LeakyReLU(0.2).
 template <int ACT>
-__device__ __forceinline__ void p2_convert_interior(float (&cur)[4][8], const float* __restrict__ ia, const float* __restrict__ is,
+__device__ __forceinline__ void p2_convert_interior(float (&cur)[8][8], const float* __restrict__ ia, const float* __restrict__ is,
                                                     int c_first, int cl_first, int chunk, uint32_t x_hi, uint32_t x_lo) {
-    float av[4], sv[4];
+    float av[8], sv[8];
     if (ACT >= 0) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { av[q] = __ldg(ia + c_first + q * 2); sv[q] = __ldg(is + c_first + q * 2); }
+        for (int q = 0; q < 8; ++q) { av[q] = __ldg(ia + c_first + q * 2); sv[q] = __ldg(is + c_first + q * 2); }
     }
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 8; ++q) {
         const int cl = cl_first + q * 2;
         float (&v)[8] = cur[q];
         if (ACT >= 0) {
@@ -105,13 +105,13 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
     const uint32_t stage_addr = (raw0 + 1023u) & ~1023u;                    // P2_STAGES x [Xh | Xl]
     const uint32_t raw_addr = stage_addr + P2_STAGES * P2_STAGE;            // P2_RAW x [64 channels][128 points] f32
     const uint32_t bar_base = raw_addr + P2_RAW * P2_RAW_BYTES;
-    const uint32_t bar_x_full = bar_base;                      // [STAGES] 8 producer warps arrive
+    const uint32_t bar_x_full = bar_base;                      // [STAGES] the 4 producer warps of the box's group arrive
     const uint32_t bar_x_empty = bar_x_full + 8 * P2_STAGES;   // [STAGES] MMA commit
     const uint32_t bar_d_full = bar_x_empty + 8 * P2_STAGES;   // [2] MMA commit
     const uint32_t bar_d_empty = bar_d_full + 16;              // [2] 128 epilogue threads
     const uint32_t bar_w_full = bar_d_empty + 16;              // 128 epilogue threads have written the weights
     const uint32_t bar_r_full = bar_w_full + 8;                // [RAW] TMA bytes
-    const uint32_t bar_r_empty = bar_r_full + 8 * P2_RAW;      // [RAW] 8 producer warps have read the box
+    const uint32_t bar_r_empty = bar_r_full + 8 * P2_RAW;      // [RAW] the 4 producer warps of the box's group have read it
     const uint32_t tmem_slot = bar_r_empty + 8 * P2_RAW;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - raw0));
 
@@ -123,10 +123,10 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
     const int my_tiles = ((int)blockIdx.x < total_tiles) ? (total_tiles - 1 - (int)blockIdx.x) / G + 1 : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P2_STAGES; ++s) { mbar_init(bar_x_full + 8 * s, 8); mbar_init(bar_x_empty + 8 * s, 1); }
+        for (int s = 0; s < P2_STAGES; ++s) { mbar_init(bar_x_full + 8 * s, 4); mbar_init(bar_x_empty + 8 * s, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(bar_d_full + 8 * i, 1); mbar_init(bar_d_empty + 8 * i, 128); }
         mbar_init(bar_w_full, 128);
-        for (int s = 0; s < P2_RAW; ++s) { mbar_init(bar_r_full + 8 * s, 1); mbar_init(bar_r_empty + 8 * s, 8); }
+        for (int s = 0; s < P2_RAW; ++s) { mbar_init(bar_r_full + 8 * s, 1); mbar_init(bar_r_empty + 8 * s, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -187,60 +187,62 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
         }
     } else if (warp >= 2 && warp < 10) {
         // ============================================================ producers: activations -> FP16 hi/lo MN-major image
-        const int pw = warp - 2;                                 // 0..7: eight channels of every 64-channel chunk
+        // Two groups of four warps take alternate boxes (group g: boxes it = g, g + 2, ...), so that two boxes are always
+        // in conversion: one group's waits (raw box full, scale / shift loads, operand stage free) overlap the other's math.
+        // Within a box a warp owns 16 channel rows, a thread 8 of them x 8 consecutive points.
+        const int pw = warp - 2, group = pw >> 2, sub = pw & 3;
         const int chunk = lane & 15;                             // 8 consecutive points
-        int it = 0;
-        for (int t = 0; t < my_tiles; ++t) {
+        const int total = my_tiles * nk;
+        for (int it = group; it < total; it += 2) {
+            const int t = it / nk, kc = it - t * nk;
             const int tile = (int)blockIdx.x + t * G;
             const int b = tile / p.tiles_per_cloud, n0 = (tile % p.tiles_per_cloud) * P2_N;
             const int pt = n0 + chunk * 8;
             const float* ia = p.in_a ? p.in_a + (long long)b * p.Cin : nullptr;
             const float* is = p.in_s ? p.in_s + (long long)b * p.Cin : nullptr;
-            for (int kc = 0; kc < nk; ++kc, ++it) {
-                const int s = it % P2_STAGES, rs = it % P2_RAW;
-                // this thread's 4 channel rows x 8 points of the raw box ([channel][128 points] f32, 512-B rows)
-                float cur[4][8];
-                mbar_wait(bar_r_full + 8 * rs, (it / P2_RAW) & 1);
+            const int s = it % P2_STAGES, rs = it % P2_RAW;
+            const int cl0 = sub * 16 + (lane >> 4);              // this thread's rows of the box: cl0 + 2 q, q = 0..7
+            // raw box: [channel][128 points] f32, 512-B rows
+            float cur[8][8];
+            mbar_wait(bar_r_full + 8 * rs, (it / P2_RAW) & 1);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t ra = raw_addr + rs * P2_RAW_BYTES + (uint32_t)(pw * 8 + q * 2 + (lane >> 4)) * 512u + (uint32_t)chunk * 32u;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][0]), "=f"(cur[q][1]), "=f"(cur[q][2]), "=f"(cur[q][3]) : "r"(ra));
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][4]), "=f"(cur[q][5]), "=f"(cur[q][6]), "=f"(cur[q][7]) : "r"(ra + 16u));
-                }
-                if (it >= P2_STAGES) mbar_wait(bar_x_empty + 8 * s, ((it / P2_STAGES) - 1) & 1);
-                const uint32_t x_hi = stage_addr + s * P2_STAGE, x_lo = x_hi + P2_PART;
-                const int cl0 = pw * 8 + (lane >> 4);                                   // this thread's first row of the box
-                if (n0 + P2_N <= p.N && kc * P2_KC + P2_KC <= p.Cin) {                   // interior box (CTA-uniform)
-                    const int c0 = kc * P2_KC + cl0;
-                    if (!ia) p2_convert_interior<-1>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
-                    else if (p.in_act == 1) p2_convert_interior<1>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
-                    else if (p.in_act == 2) p2_convert_interior<2>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
-                    else p2_convert_interior<0>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int cl = cl0 + q * 2;                  // channel within the chunk = row of the image
-                        const int c = kc * P2_KC + cl;
-                        float (&v)[8] = cur[q];
-                        if (c >= p.Cin) {
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = 0.f;
-                        } else if (ia) {
-                            const float av = __ldg(ia + c), sv = __ldg(is + c);
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) v[e] = (pt + e < p.N) ? p2_act(fmaf(av, v[e], sv), p.in_act) : 0.f;
-                        }
-                        // image: [half = point / 64][row = channel][128 B = 64 points], 16-byte chunks XOR-swizzled by (row & 7)
-                        const uint32_t off = (uint32_t)(chunk >> 3) * (P2_PART / 2) + (uint32_t)cl * 128u +
-                                             (uint32_t)(((chunk & 7) ^ (cl & 7)) << 4);
-                        p2_split_store(v, x_hi + off, x_lo + off);
-                    }
-                }
-                // generic-proxy writes of the image -> tensor-core reads; generic-proxy reads of the raw box -> TMA's next write
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(bar_x_full + 8 * s); mbar_arrive(bar_r_empty + 8 * rs); }
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t ra = raw_addr + rs * P2_RAW_BYTES + (uint32_t)(cl0 + q * 2) * 512u + (uint32_t)chunk * 32u;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][0]), "=f"(cur[q][1]), "=f"(cur[q][2]), "=f"(cur[q][3]) : "r"(ra));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][4]), "=f"(cur[q][5]), "=f"(cur[q][6]), "=f"(cur[q][7]) : "r"(ra + 16u));
             }
+            if (it >= P2_STAGES) mbar_wait(bar_x_empty + 8 * s, ((it / P2_STAGES) - 1) & 1);
+            const uint32_t x_hi = stage_addr + s * P2_STAGE, x_lo = x_hi + P2_PART;
+            if (n0 + P2_N <= p.N && kc * P2_KC + P2_KC <= p.Cin) {                   // interior box (CTA-uniform)
+                const int c0 = kc * P2_KC + cl0;
+                if (!ia) p2_convert_interior<-1>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
+                else if (p.in_act == 1) p2_convert_interior<1>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
+                else if (p.in_act == 2) p2_convert_interior<2>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
+                else p2_convert_interior<0>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int cl = cl0 + q * 2;                  // channel within the chunk = row of the image
+                    const int c = kc * P2_KC + cl;
+                    float (&v)[8] = cur[q];
+                    if (c >= p.Cin) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                    } else if (ia) {
+                        const float av = __ldg(ia + c), sv = __ldg(is + c);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[e] = (pt + e < p.N) ? p2_act(fmaf(av, v[e], sv), p.in_act) : 0.f;
+                    }
+                    // image: [half = point / 64][row = channel][128 B = 64 points], 16-byte chunks XOR-swizzled by (row & 7)
+                    const uint32_t off = (uint32_t)(chunk >> 3) * (P2_PART / 2) + (uint32_t)cl * 128u +
+                                         (uint32_t)(((chunk & 7) ^ (cl & 7)) << 4);
+                    p2_split_store(v, x_hi + off, x_lo + off);
+                }
+            }
+            // generic-proxy writes of the image -> tensor-core reads; generic-proxy reads of the raw box -> TMA's next write
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(bar_x_full + 8 * s); mbar_arrive(bar_r_empty + 8 * rs); }
         }
     } else if (warp >= 10) {
         // ============================================================ epilogue warps: thread = output channel

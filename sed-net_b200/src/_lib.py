@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libsednet_b200.so")
+LIB_PATH = os.environ.get("SEDNET_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libsednet_b200.so")   # override: A/B builds
 
 c_f32p, c_i32p, c_i64p, c_vp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
 I, F, L, D = C.c_int, C.c_float, C.c_int64, C.c_double
