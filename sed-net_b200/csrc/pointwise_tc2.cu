@@ -36,6 +36,7 @@ constexpr int P2_KMAX = 256;             // input channels held in tensor memory
 constexpr uint32_t P2_PART = P2_N * P2_KC * 2;       // 16 KB: [2 halves of 64 points][64 channels][64 points] fp16
 constexpr uint32_t P2_STAGE = 2 * P2_PART;            // hi + lo
 constexpr uint32_t P2_RAW_BYTES = P2_N * P2_KC * 4;   // 32 KB: [64 channels][128 points] f32
+constexpr uint32_t P2_TR_BYTES = 32 * 33 * 4;         // one epilogue warp's transpose scratch
 constexpr uint32_t P2_COL_D = 256;                    // accumulators at columns [256,384) and [384,512)
 
 struct P2Params {
@@ -104,7 +105,8 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
     const uint32_t raw0 = smem_u32(smem_raw);
     const uint32_t stage_addr = (raw0 + 1023u) & ~1023u;                    // P2_STAGES x [Xh | Xl]
     const uint32_t raw_addr = stage_addr + P2_STAGES * P2_STAGE;            // P2_RAW x [64 channels][128 points] f32
-    const uint32_t bar_base = raw_addr + P2_RAW * P2_RAW_BYTES;
+    const uint32_t tr_addr = raw_addr + P2_RAW * P2_RAW_BYTES;              // 4 epilogue warps x [32 channels][33] f32 (store transpose)
+    const uint32_t bar_base = tr_addr + 4 * P2_TR_BYTES;
     const uint32_t bar_x_full = bar_base;                      // [STAGES] the 4 producer warps of the box's group arrive
     const uint32_t bar_x_empty = bar_x_full + 8 * P2_STAGES;   // [STAGES] MMA commit
     const uint32_t bar_d_full = bar_x_empty + 8 * P2_STAGES;   // [2] MMA commit
@@ -314,9 +316,9 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
                     }
                 }
                 ds1 += (double)s1; ds2 += (double)s2;
-                if (p.Y && cvalid) {
+                if (p.Y && cvalid && p.y_point_major) {
                     float* Yb = p.Y + (long long)b * p.y_bstride;
-                    if (p.y_point_major) {
+                    {
                         float* o = Yb + (long long)nb * p.ldy + co;                                 // lanes = consecutive channels
                         if (nb + 32 <= p.N) {
 #pragma unroll
@@ -326,16 +328,40 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
                             for (int i = 0; i < 32; ++i)
                                 if (nb + i < p.N) o[(long long)i * p.ldy] = y[i];
                         }
-                    } else {
-                        float* o = Yb + (long long)co * p.ldy + nb;
-                        if (nb + 31 < p.N && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    }
+                }
+                if (p.Y && !p.y_point_major) {
+                    // channel-major output: a thread owns one channel row, so a direct store scatters 32 x 16 B per warp
+                    // instruction over 32 rows (32 LSU wavefronts each: the 4096 store cycles per tile were what bounded the
+                    // layers that write Y).  Interior chunks go through a 32 x 33 shared-memory transpose instead: every store
+                    // instruction then writes 4 rows x 128 contiguous bytes.
+                    float* Yb = p.Y + (long long)b * p.y_bstride;
+                    const int cb = co0 + quarter * 32;                                   // the warp's first channel
+                    float* ob = Yb + (long long)cb * p.ldy + nb;
+                    const bool fast = (nb + 32 <= p.N) && (cb + 32 <= p.Cout) && ((p.ldy & 3) == 0) &&
+                                      ((reinterpret_cast<uintptr_t>(ob) & 15) == 0);
+                    if (fast) {                                                          // warp-uniform
+                        const uint32_t sc = tr_addr + (uint32_t)(warp - 10) * P2_TR_BYTES;
 #pragma unroll
-                            for (int i = 0; i < 8; ++i)
-                                reinterpret_cast<float4*>(o)[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
-                        } else {
+                        for (int i = 0; i < 32; ++i)
+                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sc + (uint32_t)(lane * 33 + i) * 4u), "f"(y[i]));
+                        __syncwarp();
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) if (nb + i < p.N) o[i] = y[i];
+                        for (int r4 = 0; r4 < 8; ++r4) {
+                            const int rrow = r4 * 4 + (lane >> 3), col = (lane & 7) * 4;
+                            float4 o4;
+                            const uint32_t sa = sc + (uint32_t)(rrow * 33 + col) * 4u;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o4.x) : "r"(sa));
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o4.y) : "r"(sa + 4u));
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o4.z) : "r"(sa + 8u));
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o4.w) : "r"(sa + 12u));
+                            *reinterpret_cast<float4*>(ob + (long long)rrow * p.ldy + col) = o4;
                         }
+                        __syncwarp();
+                    } else if (cvalid) {
+                        float* o = Yb + (long long)co * p.ldy + nb;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) if (nb + i < p.N) o[i] = y[i];
                     }
                 }
             }
@@ -399,7 +425,7 @@ int pw_gemm_tc2(const float* X, long long x_bstride, int ldx, const float* Wt, i
     }
     P2Params p{X, x_bstride, ldx, Wh, Wl, rscale, bias, bias_bstride, in_a, in_s, in_act, Y, y_bstride, ldy, y_point_major,
                stats, mm, Cin, Cout, N, kpad, B, tiles_per_cloud, G};
-    constexpr size_t smem = (size_t)P2_STAGES * P2_STAGE + (size_t)P2_RAW * P2_RAW_BYTES + 1024 + 256;
+    constexpr size_t smem = (size_t)P2_STAGES * P2_STAGE + (size_t)P2_RAW * P2_RAW_BYTES + 4 * P2_TR_BYTES + 1024 + 256;
     static_assert(smem <= 227 * 1024, "shared memory budget");
     cudaError_t e = cudaFuncSetAttribute(pw_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) rc = SED_ERR_CUDA_BASE - (int)e;
