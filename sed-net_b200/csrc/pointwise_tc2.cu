@@ -36,7 +36,8 @@ constexpr int P2_KMAX = 256;             // input channels held in tensor memory
 constexpr uint32_t P2_PART = P2_N * P2_KC * 2;       // 16 KB: [2 halves of 64 points][64 channels][64 points] fp16
 constexpr uint32_t P2_STAGE = 2 * P2_PART;            // hi + lo
 constexpr uint32_t P2_RAW_BYTES = P2_N * P2_KC * 4;   // 32 KB: [64 channels][128 points] f32
-constexpr uint32_t P2_TR_BYTES = 32 * 33 * 4;         // one epilogue warp's transpose scratch
+constexpr uint32_t P2_TR_PITCH = 36;                  // floats per scratch row: 144 B keeps 16-byte accesses aligned and conflict-free
+constexpr uint32_t P2_TR_BYTES = 32 * P2_TR_PITCH * 4; // one epilogue warp's transpose scratch
 constexpr uint32_t P2_COL_D = 256;                    // accumulators at columns [256,384) and [384,512)
 
 struct P2Params {
@@ -56,8 +57,15 @@ __device__ __forceinline__ float p2_act(float v, int act) {
     return v;
 }
 
-// FP16 hi / lo split of 8 consecutive points of one channel row and its two 16-byte stores into the operand image
-__device__ __forceinline__ void p2_split_store(const float (&v)[8], uint32_t hi_addr, uint32_t lo_addr) {
+// A thread owns 8 consecutive points of a channel row = two 16-byte pieces of the raw box.  With a 32-byte lane stride, reading
+// "first piece, then second piece" puts lanes c and c + 4 of a quarter-warp on the same banks (2-way conflict on every raw
+// LDS.128).  Lanes with sel = 1 therefore read their pieces in the opposite order: v[0..3] holds piece `sel`, v[4..7] piece
+// `1 - sel` (conflict-free in both loads), and the FP16 image gets two 8-byte stores whose order follows `sel` (sel also
+// flips between the two 64-point halves, so the half-warps of the STS.64 stay conflict-free).
+__device__ __forceinline__ int p2_sel(int chunk) { return ((chunk >> 2) ^ (chunk >> 3)) & 1; }
+
+// FP16 hi / lo split of the 8 points and their stores into the operand image (16-byte chunk at hi_addr / lo_addr)
+__device__ __forceinline__ void p2_split_store(const float (&v)[8], uint32_t hi_addr, uint32_t lo_addr, int sel) {
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -67,8 +75,11 @@ __device__ __forceinline__ void p2_split_store(const float (&v)[8], uint32_t hi_
         hi[e] = *reinterpret_cast<const uint32_t*>(&h);
         lo[e] = *reinterpret_cast<const uint32_t*>(&l);
     }
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(hi_addr), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]));
-    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(lo_addr), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]));
+    const uint32_t o0 = (uint32_t)sel * 8u, o1 = 8u - o0;      // where v[0..3] and v[4..7] belong inside the 16-byte chunk
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(hi_addr + o0), "r"(hi[0]), "r"(hi[1]));
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(hi_addr + o1), "r"(hi[2]), "r"(hi[3]));
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(lo_addr + o0), "r"(lo[0]), "r"(lo[1]));
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(lo_addr + o1), "r"(lo[2]), "r"(lo[3]));
 }
 
 // Interior boxes (all 128 points and all 64 channels exist -- every box but those of a cloud's last tile): no bounds tests,
@@ -76,7 +87,7 @@ __device__ __forceinline__ void p2_split_store(const float (&v)[8], uint32_t hi_
 // 1 affine + ReLU, 2 affine + LeakyReLU(0.2).
 template <int ACT>
 __device__ __forceinline__ void p2_convert_interior(float (&cur)[8][8], const float* __restrict__ ia, const float* __restrict__ is,
-                                                    int c_first, int cl_first, int chunk, uint32_t x_hi, uint32_t x_lo) {
+                                                    int c_first, int cl_first, int chunk, uint32_t x_hi, uint32_t x_lo, int sel) {
     float av[8], sv[8];
     if (ACT >= 0) {
 #pragma unroll
@@ -96,7 +107,7 @@ __device__ __forceinline__ void p2_convert_interior(float (&cur)[8][8], const fl
             }
         }
         const uint32_t off = (uint32_t)(chunk >> 3) * (P2_PART / 2) + (uint32_t)cl * 128u + (uint32_t)(((chunk & 7) ^ (cl & 7)) << 4);
-        p2_split_store(v, x_hi + off, x_lo + off);
+        p2_split_store(v, x_hi + off, x_lo + off, sel);
     }
 }
 
@@ -105,7 +116,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
     const uint32_t raw0 = smem_u32(smem_raw);
     const uint32_t stage_addr = (raw0 + 1023u) & ~1023u;                    // P2_STAGES x [Xh | Xl]
     const uint32_t raw_addr = stage_addr + P2_STAGES * P2_STAGE;            // P2_RAW x [64 channels][128 points] f32
-    const uint32_t tr_addr = raw_addr + P2_RAW * P2_RAW_BYTES;              // 4 epilogue warps x [32 channels][33] f32 (store transpose)
+    const uint32_t tr_addr = raw_addr + P2_RAW * P2_RAW_BYTES;              // 4 epilogue warps x [32 channels][36] f32 (store transpose)
     const uint32_t bar_base = tr_addr + 4 * P2_TR_BYTES;
     const uint32_t bar_x_full = bar_base;                      // [STAGES] the 4 producer warps of the box's group arrive
     const uint32_t bar_x_empty = bar_x_full + 8 * P2_STAGES;   // [STAGES] MMA commit
@@ -194,6 +205,8 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
         // Within a box a warp owns 16 channel rows, a thread 8 of them x 8 consecutive points.
         const int pw = warp - 2, group = pw >> 2, sub = pw & 3;
         const int chunk = lane & 15;                             // 8 consecutive points
+        const int sel = p2_sel(chunk);                           // which of its two raw pieces this lane reads first
+        const uint32_t so = (uint32_t)sel * 16u;
         const int total = my_tiles * nk;
         for (int it = group; it < total; it += 2) {
             const int t = it / nk, kc = it - t * nk;
@@ -210,17 +223,17 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const uint32_t ra = raw_addr + rs * P2_RAW_BYTES + (uint32_t)(cl0 + q * 2) * 512u + (uint32_t)chunk * 32u;
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][0]), "=f"(cur[q][1]), "=f"(cur[q][2]), "=f"(cur[q][3]) : "r"(ra));
-                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][4]), "=f"(cur[q][5]), "=f"(cur[q][6]), "=f"(cur[q][7]) : "r"(ra + 16u));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][0]), "=f"(cur[q][1]), "=f"(cur[q][2]), "=f"(cur[q][3]) : "r"(ra + so));
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][4]), "=f"(cur[q][5]), "=f"(cur[q][6]), "=f"(cur[q][7]) : "r"(ra + 16u - so));
             }
             if (it >= P2_STAGES) mbar_wait(bar_x_empty + 8 * s, ((it / P2_STAGES) - 1) & 1);
             const uint32_t x_hi = stage_addr + s * P2_STAGE, x_lo = x_hi + P2_PART;
             if (n0 + P2_N <= p.N && kc * P2_KC + P2_KC <= p.Cin) {                   // interior box (CTA-uniform)
                 const int c0 = kc * P2_KC + cl0;
-                if (!ia) p2_convert_interior<-1>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
-                else if (p.in_act == 1) p2_convert_interior<1>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
-                else if (p.in_act == 2) p2_convert_interior<2>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
-                else p2_convert_interior<0>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo);
+                if (!ia) p2_convert_interior<-1>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo, sel);
+                else if (p.in_act == 1) p2_convert_interior<1>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo, sel);
+                else if (p.in_act == 2) p2_convert_interior<2>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo, sel);
+                else p2_convert_interior<0>(cur, ia, is, c0, cl0, chunk, x_hi, x_lo, sel);
             } else {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
@@ -233,12 +246,15 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
                     } else if (ia) {
                         const float av = __ldg(ia + c), sv = __ldg(is + c);
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) v[e] = (pt + e < p.N) ? p2_act(fmaf(av, v[e], sv), p.in_act) : 0.f;
+                        for (int e = 0; e < 8; ++e) {
+                            const int pe = pt + ((e < 4) ? e + 4 * sel : e - 4 * sel);       // the point v[e] holds
+                            v[e] = (pe < p.N) ? p2_act(fmaf(av, v[e], sv), p.in_act) : 0.f;
+                        }
                     }
                     // image: [half = point / 64][row = channel][128 B = 64 points], 16-byte chunks XOR-swizzled by (row & 7)
                     const uint32_t off = (uint32_t)(chunk >> 3) * (P2_PART / 2) + (uint32_t)cl * 128u +
                                          (uint32_t)(((chunk & 7) ^ (cl & 7)) << 4);
-                    p2_split_store(v, x_hi + off, x_lo + off);
+                    p2_split_store(v, x_hi + off, x_lo + off, sel);
                 }
             }
             // generic-proxy writes of the image -> tensor-core reads; generic-proxy reads of the raw box -> TMA's next write
@@ -333,7 +349,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
                 if (p.Y && !p.y_point_major) {
                     // channel-major output: a thread owns one channel row, so a direct store scatters 32 x 16 B per warp
                     // instruction over 32 rows (32 LSU wavefronts each: the 4096 store cycles per tile were what bounded the
-                    // layers that write Y).  Interior chunks go through a 32 x 33 shared-memory transpose instead: every store
+                    // layers that write Y).  Interior chunks go through a 32 x 36 shared-memory transpose instead: every store
                     // instruction then writes 4 rows x 128 contiguous bytes.
                     float* Yb = p.Y + (long long)b * p.y_bstride;
                     const int cb = co0 + quarter * 32;                                   // the warp's first channel
@@ -343,18 +359,16 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
                     if (fast) {                                                          // warp-uniform
                         const uint32_t sc = tr_addr + (uint32_t)(warp - 10) * P2_TR_BYTES;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            asm volatile("st.shared.f32 [%0], %1;" ::"r"(sc + (uint32_t)(lane * 33 + i) * 4u), "f"(y[i]));
+                        for (int i = 0; i < 8; ++i)
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sc + (uint32_t)(lane * P2_TR_PITCH + 4 * i) * 4u),
+                                         "f"(y[4 * i]), "f"(y[4 * i + 1]), "f"(y[4 * i + 2]), "f"(y[4 * i + 3]));
                         __syncwarp();
 #pragma unroll
                         for (int r4 = 0; r4 < 8; ++r4) {
                             const int rrow = r4 * 4 + (lane >> 3), col = (lane & 7) * 4;
                             float4 o4;
-                            const uint32_t sa = sc + (uint32_t)(rrow * 33 + col) * 4u;
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o4.x) : "r"(sa));
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o4.y) : "r"(sa + 4u));
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o4.z) : "r"(sa + 8u));
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(o4.w) : "r"(sa + 12u));
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o4.x), "=f"(o4.y), "=f"(o4.z), "=f"(o4.w)
+                                         : "r"(sc + (uint32_t)(rrow * P2_TR_PITCH + col) * 4u));
                             *reinterpret_cast<float4*>(ob + (long long)rrow * p.ldy + col) = o4;
                         }
                         __syncwarp();
