@@ -147,6 +147,16 @@ int sed_edgeconv_forward(const float* x, int64_t x_bstride, const int* idx, cons
                          const float* beta, int B, int Cin, int Cout, int N, int k, int G, float eps, float slope,
                          float* out, int64_t out_bstride, void* workspace, sed_stream_t stream);
 
+/* One 1x1 convolution of the network, src/SEDNet.py:292-342 (torch.nn.Conv1d(Cin, Cout, 1) applied to the
+ * GroupNorm + activation of the previous layer):  y[b,co,n] = bias[co] + sum_c W[co,c] * act(in_a[b,c] * x[b,c,n] + in_s[b,c]).
+ * x (B,Cin,N) with batch stride x_bstride elements, W (Cout,Cin) row pitch ldw, bias (Cout) or NULL, in_a / in_s (B,Cin)
+ * the folded GroupNorm scale / shift of the input (both NULL: x is used as is), in_act 0 none, 1 ReLU, 2 LeakyReLU(0.2).
+ * y (B,Cout,N) with batch stride y_bstride.  Optional epilogue outputs: stats (B, ceil(N/128), ceil(Cout/32), 2) doubles =
+ * per 128-point tile and 32-channel block the sum and sum of squares of y; mm (B, ceil(N/128), Cout, 2) = max and min. */
+int sed_pointwise_forward(const float* x, int64_t x_bstride, const float* W, int ldw, const float* bias, const float* in_a,
+                          const float* in_s, int in_act, float* y, int64_t y_bstride, double* stats, float* mm, int B,
+                          int Cin, int Cout, int N, sed_stream_t stream);
+
 /* ------------------------------------------------------------------ mean-shift (src/mean_shift.py) */
 
 /* F.normalize(embedding[b].T, p=2, dim=1) (generate_predictions_aug.py:379-380): emb (B,d,N) -> X (B,N,d). */

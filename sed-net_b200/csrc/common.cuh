@@ -3,6 +3,8 @@
 #include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #define SED_OK 0
 #define SED_ERR_ARG (-1)
@@ -21,10 +23,24 @@ extern std::atomic<long long> g_sed_launches;
         if (e__ != cudaSuccess) return SED_ERR_CUDA_BASE - (int)e__; \
     } while (0)
 
-#define SED_TRY(call)                                        \
-    do {                                                     \
-        int rc__ = (call);                                   \
-        if (rc__ != SED_OK) return rc__;                     \
+// SEDNET_B200_DEBUG_SYNC=1: synchronise the device after every step and name the first one that faults (debugging aid)
+inline bool sed_debug_sync() {
+    static const bool on = getenv("SEDNET_B200_DEBUG_SYNC") != nullptr;
+    return on;
+}
+
+#define SED_TRY(call)                                                                         \
+    do {                                                                                      \
+        int rc__ = (call);                                                                    \
+        if (rc__ != SED_OK) return rc__;                                                      \
+        if (sed_debug_sync()) {                                                               \
+            cudaError_t se__ = cudaDeviceSynchronize();                                       \
+            if (se__ != cudaSuccess) {                                                        \
+                fprintf(stderr, "[sednet_b200] %s:%d %s -> %s\n", __FILE__, __LINE__, #call, \
+                        cudaGetErrorString(se__));                                            \
+                return SED_ERR_CUDA_BASE - (int)se__;                                         \
+            }                                                                                 \
+        }                                                                                     \
     } while (0)
 
 #define SED_CUDA(call)                                       \

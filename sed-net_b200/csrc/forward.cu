@@ -141,6 +141,14 @@ int64_t sed_sednet_workspace_bytes(int B, int N, int k) {
     return A.off;
 }
 
+int sed_pointwise_forward(const float* x, int64_t x_bstride, const float* W, int ldw, const float* bias, const float* in_a,
+                          const float* in_s, int in_act, float* y, int64_t y_bstride, double* stats, float* mm, int B,
+                          int Cin, int Cout, int N, sed_stream_t stream) {
+    if (!x || !W || !y || in_act < 0 || in_act > 2 || ldw < Cin) return SED_ERR_ARG;
+    return pw_gemm(x, x_bstride, N, W, ldw, bias, 0, in_a, in_s, in_act, y, y_bstride, N, 0, stats, mm, B, Cin, Cout, N,
+                   (cudaStream_t)stream);
+}
+
 int sed_sednet_forward(const float* const* P, const float* points, int B, int N, int k, float normal_metric_W,
                        float w_pos_enc, int E, int NP, float* embedding, float* log_prob, float* edges, float* x4_out,
                        float* feats_out, void* workspace, int64_t workspace_bytes, sed_stream_t stream) {

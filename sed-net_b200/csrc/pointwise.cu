@@ -426,6 +426,50 @@ __global__ void graph_feature_kernel(const float* __restrict__ x, const long lon
     }
 }
 
+// Narrow outputs (the two logit layers of the heads, src/SEDNet.py:313 mlp_prim_prob2 256 -> 6 and :317 edge_module.2 128 -> 2):
+// next to no arithmetic, so a tensor-core tile is all overhead (60 / 45 us on pw_tc_kernel for 0.06 us of MMA work).  One
+// thread per point walks the channels (coalesced along the points), applies the producer's affine + activation and keeps the
+// <= 8 sums in registers; the weights sit in shared memory.  Bound by reading the input once.
+constexpr int PWS_MAX_COUT = 8, PWS_THREADS = 256;
+
+__global__ void __launch_bounds__(PWS_THREADS) pw_small_kernel(PwParams p) {
+    extern __shared__ float sm[];                      // W [Cout][Cin] | a [Cin] | s [Cin]
+    float* Ws = sm;
+    float* as_ = Ws + p.Cout * p.Cin;
+    float* ss = as_ + p.Cin;
+    const int b = blockIdx.y, n = blockIdx.x * PWS_THREADS + threadIdx.x;
+    for (int e = threadIdx.x; e < p.Cout * p.Cin; e += PWS_THREADS) Ws[e] = p.Wt[(long long)(e / p.Cin) * p.ldw + e % p.Cin];
+    for (int c = threadIdx.x; c < p.Cin; c += PWS_THREADS) {
+        as_[c] = p.in_a ? p.in_a[(long long)b * p.Cin + c] : 1.f;
+        ss[c] = p.in_s ? p.in_s[(long long)b * p.Cin + c] : 0.f;
+    }
+    __syncthreads();
+    if (n >= p.N) return;
+    const float* X = p.X + (long long)b * p.x_bstride + n;
+    float acc[PWS_MAX_COUT];
+#pragma unroll
+    for (int co = 0; co < PWS_MAX_COUT; ++co) acc[co] = 0.f;
+    const bool affine = p.in_a != nullptr;
+#pragma unroll 4
+    for (int c = 0; c < p.Cin; ++c) {
+        float v = __ldg(X + (long long)c * p.ldx);
+        if (affine) v = apply_act(fmaf(as_[c], v, ss[c]), p.in_act);
+#pragma unroll
+        for (int co = 0; co < PWS_MAX_COUT; ++co)
+            if (co < p.Cout) acc[co] = fmaf(Ws[co * p.Cin + c], v, acc[co]);
+    }
+    float* Y = p.Y + (long long)b * p.y_bstride;
+#pragma unroll
+    for (int co = 0; co < PWS_MAX_COUT; ++co) {
+        if (co < p.Cout) {
+            const float bv = p.bias ? p.bias[(long long)b * p.bias_bstride + co] : 0.f;
+            const float y = __fadd_rn(acc[co], bv);
+            if (p.y_point_major) Y[(long long)n * p.ldy + co] = y;
+            else Y[(long long)co * p.ldy + n] = y;
+        }
+    }
+}
+
 int pw_gemm(const float* X, long long x_bstride, int ldx, const float* Wt, int ldw, const float* bias,
             long long bias_bstride, const float* in_a, const float* in_s, int in_act, float* Y, long long y_bstride,
             int ldy, int y_point_major, double* stats, float* mm, int B, int Cin, int Cout, int N, cudaStream_t stream) {
@@ -433,6 +477,13 @@ int pw_gemm(const float* X, long long x_bstride, int ldx, const float* Wt, int l
     if ((in_a == nullptr) != (in_s == nullptr)) return SED_ERR_ARG;
     // SEDNET_B200_PW=ffma forces the CUDA-core kernel of this file (A/B comparisons); default: tensor cores
     static const bool ffma = [] { const char* e = getenv("SEDNET_B200_PW"); return e && !strcmp(e, "ffma"); }();
+    if (!ffma && Cout <= PWS_MAX_COUT && Cin >= 32 && Y && !stats && !mm && (size_t)(Cout + 2) * Cin * sizeof(float) <= 48 * 1024) {
+        PwParams ps{X, x_bstride, ldx, Wt, ldw, bias, bias_bstride, in_a, in_s, in_act, Y, y_bstride, ldy, y_point_major,
+                    nullptr, nullptr, Cin, Cout, N};
+        pw_small_kernel<<<dim3((N + PWS_THREADS - 1) / PWS_THREADS, B), PWS_THREADS, (size_t)(Cout + 2) * Cin * sizeof(float), stream>>>(ps);
+        SED_CHECK_LAUNCH();
+        return SED_OK;
+    }
     // SEDNET_B200_PW=tc1 keeps every shape on the first tensor-core kernel (one tile per CTA, pointwise_tc.cu)
     static const bool tc1 = [] { const char* e = getenv("SEDNET_B200_PW"); return e && !strcmp(e, "tc1"); }();
     if (!ffma && !tc1) {

@@ -217,6 +217,14 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
             const float* is = p.in_s ? p.in_s + (long long)b * p.Cin : nullptr;
             const int s = it % P2_STAGES, rs = it % P2_RAW;
             const int cl0 = sub * 16 + (lane >> 4);              // this thread's rows of the box: cl0 + 2 q, q = 0..7
+            // Operand stage first, raw box second.  A parity wait is only meaningful on a barrier that is at most one phase
+            // behind, and the previous box of this raw slot (it - 3) belonged to the OTHER group: nothing this warp has seen
+            // so far proves that box landed (TMA boxes may complete out of order), and a wait for phase k on a barrier still
+            // in phase k - 1 returns at once.  The stage wait closes that: stage s free => the MMA consumed box it - 3 => both
+            // groups read every box <= it - 3 (their r_empty arrivals precede their x_full arrivals) => r_full[rs] is in
+            // phase k.  (Boxes 0..2 wait for phase 0 of fresh barriers.)
+            static_assert(P2_RAW >= P2_STAGES, "the stage wait must cover the raw slot's previous box");
+            if (it >= P2_STAGES) mbar_wait(bar_x_empty + 8 * s, ((it / P2_STAGES) - 1) & 1);
             // raw box: [channel][128 points] f32, 512-B rows
             float cur[8][8];
             mbar_wait(bar_r_full + 8 * rs, (it / P2_RAW) & 1);
@@ -226,7 +234,6 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][0]), "=f"(cur[q][1]), "=f"(cur[q][2]), "=f"(cur[q][3]) : "r"(ra + so));
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(cur[q][4]), "=f"(cur[q][5]), "=f"(cur[q][6]), "=f"(cur[q][7]) : "r"(ra + 16u - so));
             }
-            if (it >= P2_STAGES) mbar_wait(bar_x_empty + 8 * s, ((it / P2_STAGES) - 1) & 1);
             const uint32_t x_hi = stage_addr + s * P2_STAGE, x_lo = x_hi + P2_PART;
             if (n0 + P2_N <= p.N && kc * P2_KC + P2_KC <= p.Cin) {                   // interior box (CTA-uniform)
                 const int c0 = kc * P2_KC + cl0;
@@ -260,7 +267,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) pw_tc2_kernel(const __grid_cons
             // generic-proxy writes of the image -> tensor-core reads; generic-proxy reads of the raw box -> TMA's next write
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
-            if (lane == 0) { mbar_arrive(bar_x_full + 8 * s); mbar_arrive(bar_r_empty + 8 * rs); }
+            if (lane == 0) { mbar_arrive(bar_r_empty + 8 * rs); mbar_arrive(bar_x_full + 8 * s); }   // in this order (see above)
         }
     } else if (warp >= 10) {
         // ============================================================ epilogue warps: thread = output channel

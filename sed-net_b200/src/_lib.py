@@ -11,7 +11,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SEDNET_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libsednet_b200.so")   # override: A/B builds
 
-c_f32p, c_i32p, c_i64p, c_vp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+c_f32p, c_f64p, c_i32p, c_i64p, c_vp = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
 I, F, L, D = C.c_int, C.c_float, C.c_int64, C.c_double
 
 # name -> (restype, argtypes); order and meaning as in include/sednet_b200.h
@@ -30,6 +30,8 @@ SIGNATURES = {
     "sed_edgeconv_workspace_bytes": (L, [I, I, I]),
     "sed_edgeconv_forward": (I, [c_f32p, L, c_i32p, c_f32p, c_f32p, c_f32p, I, I, I, I, I, I, F, F, c_f32p, L, c_vp,
                                  c_vp]),
+    "sed_pointwise_forward": (I, [c_f32p, L, c_f32p, I, c_f32p, c_f32p, c_f32p, I, c_f32p, L, c_f64p, c_f32p, I, I, I, I,
+                                  c_vp]),
     "sed_normalize_transpose": (I, [c_f32p, I, I, I, c_f32p, c_vp]),
     "sed_ms_bandwidth": (I, [c_f32p, I, I, I, I, F, c_f32p, c_f32p, c_vp]),
     "sed_ms_shift": (I, [c_f32p, c_f32p, I, I, I, I, I, I, c_f32p, c_f32p, c_vp]),
