@@ -426,46 +426,102 @@ __global__ void graph_feature_kernel(const float* __restrict__ x, const long lon
     }
 }
 
-// Narrow outputs (the two logit layers of the heads, src/SEDNet.py:313 mlp_prim_prob2 256 -> 6 and :317 edge_module.2 128 -> 2):
-// next to no arithmetic, so a tensor-core tile is all overhead (60 / 45 us on pw_tc_kernel for 0.06 us of MMA work).  One
-// thread per point walks the channels (coalesced along the points), applies the producer's affine + activation and keeps the
-// <= 8 sums in registers; the weights sit in shared memory.  Bound by reading the input once.
-constexpr int PWS_MAX_COUT = 8, PWS_THREADS = 256;
+// Few-output-channel layers (Cout <= 8: src/SEDNet.py:305 mlp_prim_prob2 256 -> 6 and :317 edge_module.2 128 -> 2):
+// next to no arithmetic, so a tensor-core tile is all overhead (60 / 45 us on pw_tc_kernel for 0.06 us of MMA work) and the
+// layer is bound by reading its input once.  A CTA owns 128 points; each of its eight warps walks one eighth of the input
+// channels with 16-byte loads (a lane = 4 consecutive points, 512 contiguous bytes per warp and channel, eight loads in flight),
+// applies the producer's affine + activation and keeps 4 x Cout sums in registers against weights broadcast from shared
+// memory; the eight partial sums meet in shared memory.  (A first version with one thread per point over ALL channels ran at
+// 142 / 74 us: 550 threads per SM cannot cover the latency of 256 dependent-issue loads.)
+constexpr int PWS_MAX_COUT = 8, PWS_THREADS = 256, PWS_PTS = 128, PWS_WARPS = PWS_THREADS / 32;
 
 __global__ void __launch_bounds__(PWS_THREADS) pw_small_kernel(PwParams p) {
-    extern __shared__ float sm[];                      // W [Cout][Cin] | a [Cin] | s [Cin]
+    extern __shared__ __align__(16) float sm[];        // W [Cin][8] | a [Cin] | s [Cin] | red [8 warps][8][128]
     float* Ws = sm;
-    float* as_ = Ws + p.Cout * p.Cin;
+    float* as_ = Ws + p.Cin * PWS_MAX_COUT;
     float* ss = as_ + p.Cin;
-    const int b = blockIdx.y, n = blockIdx.x * PWS_THREADS + threadIdx.x;
-    for (int e = threadIdx.x; e < p.Cout * p.Cin; e += PWS_THREADS) Ws[e] = p.Wt[(long long)(e / p.Cin) * p.ldw + e % p.Cin];
+    float* red = ss + p.Cin;
+    const int b = blockIdx.y, n0 = blockIdx.x * PWS_PTS;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int e = threadIdx.x; e < p.Cin * PWS_MAX_COUT; e += PWS_THREADS) {
+        const int c = e >> 3, co = e & 7;
+        Ws[e] = co < p.Cout ? p.Wt[(long long)co * p.ldw + c] : 0.f;
+    }
     for (int c = threadIdx.x; c < p.Cin; c += PWS_THREADS) {
         as_[c] = p.in_a ? p.in_a[(long long)b * p.Cin + c] : 1.f;
         ss[c] = p.in_s ? p.in_s[(long long)b * p.Cin + c] : 0.f;
     }
     __syncthreads();
-    if (n >= p.N) return;
+    const int n = n0 + lane * 4;
     const float* X = p.X + (long long)b * p.x_bstride + n;
-    float acc[PWS_MAX_COUT];
+    const bool vec = ((p.ldx & 3) == 0) && ((p.x_bstride & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) &&
+                     (n + 3 < p.N);
+    float acc[PWS_MAX_COUT][4];
 #pragma unroll
-    for (int co = 0; co < PWS_MAX_COUT; ++co) acc[co] = 0.f;
+    for (int co = 0; co < PWS_MAX_COUT; ++co)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[co][e] = 0.f;
     const bool affine = p.in_a != nullptr;
-#pragma unroll 4
-    for (int c = 0; c < p.Cin; ++c) {
-        float v = __ldg(X + (long long)c * p.ldx);
-        if (affine) v = apply_act(fmaf(as_[c], v, ss[c]), p.in_act);
+    const int per = (p.Cin + PWS_WARPS - 1) / PWS_WARPS;
+    const int c_begin = warp * per, c_end = min(p.Cin, c_begin + per);
+    constexpr int U = 8;
+    for (int c0 = c_begin; c0 < c_end; c0 += U) {
+        float4 x[U];
 #pragma unroll
-        for (int co = 0; co < PWS_MAX_COUT; ++co)
-            if (co < p.Cout) acc[co] = fmaf(Ws[co * p.Cin + c], v, acc[co]);
+        for (int u = 0; u < U; ++u) {                  // all loads of the group first
+            const int c = c0 + u;
+            x[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < c_end) {
+                const float* xr = X + (long long)c * p.ldx;
+                if (vec) x[u] = __ldg(reinterpret_cast<const float4*>(xr));
+                else {
+                    if (n < p.N) x[u].x = __ldg(xr);
+                    if (n + 1 < p.N) x[u].y = __ldg(xr + 1);
+                    if (n + 2 < p.N) x[u].z = __ldg(xr + 2);
+                    if (n + 3 < p.N) x[u].w = __ldg(xr + 3);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + u;
+            if (c < c_end) {
+                float v[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+                if (affine) {
+                    const float av = as_[c], sv = ss[c];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = apply_act(fmaf(av, v[e], sv), p.in_act);
+                }
+                const float4 w0 = *reinterpret_cast<const float4*>(Ws + c * PWS_MAX_COUT);
+                const float4 w1 = *reinterpret_cast<const float4*>(Ws + c * PWS_MAX_COUT + 4);
+                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int co = 0; co < PWS_MAX_COUT; ++co)
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) acc[co][e] = fmaf(w[co], v[e], acc[co][e]);
+            }
+        }
     }
+#pragma unroll
+    for (int co = 0; co < PWS_MAX_COUT; ++co)
+        *reinterpret_cast<float4*>(red + ((warp * PWS_MAX_COUT + co) * PWS_PTS) + lane * 4) =
+            make_float4(acc[co][0], acc[co][1], acc[co][2], acc[co][3]);
+    __syncthreads();
+    // thread = (point, half of the output channels): fixed-order sum over the eight warps
+    const int pt = threadIdx.x & (PWS_PTS - 1), half = threadIdx.x >> 7;
+    const int nn = n0 + pt;
+    if (nn >= p.N) return;
     float* Y = p.Y + (long long)b * p.y_bstride;
 #pragma unroll
-    for (int co = 0; co < PWS_MAX_COUT; ++co) {
+    for (int q = 0; q < 4; ++q) {
+        const int co = half * 4 + q;
         if (co < p.Cout) {
-            const float bv = p.bias ? p.bias[(long long)b * p.bias_bstride + co] : 0.f;
-            const float y = __fadd_rn(acc[co], bv);
-            if (p.y_point_major) Y[(long long)n * p.ldy + co] = y;
-            else Y[(long long)co * p.ldy + n] = y;
+            float y = 0.f;
+#pragma unroll
+            for (int w = 0; w < PWS_WARPS; ++w) y += red[(w * PWS_MAX_COUT + co) * PWS_PTS + pt];
+            y = __fadd_rn(y, p.bias ? p.bias[(long long)b * p.bias_bstride + co] : 0.f);
+            if (p.y_point_major) Y[(long long)nn * p.ldy + co] = y;
+            else Y[(long long)co * p.ldy + nn] = y;
         }
     }
 }
@@ -477,10 +533,13 @@ int pw_gemm(const float* X, long long x_bstride, int ldx, const float* Wt, int l
     if ((in_a == nullptr) != (in_s == nullptr)) return SED_ERR_ARG;
     // SEDNET_B200_PW=ffma forces the CUDA-core kernel of this file (A/B comparisons); default: tensor cores
     static const bool ffma = [] { const char* e = getenv("SEDNET_B200_PW"); return e && !strcmp(e, "ffma"); }();
-    if (!ffma && Cout <= PWS_MAX_COUT && Cin >= 32 && Y && !stats && !mm && (size_t)(Cout + 2) * Cin * sizeof(float) <= 48 * 1024) {
+    if (!ffma && Cout <= PWS_MAX_COUT && Cin >= 32 && Cin <= 1024 && Y && !stats && !mm) {
         PwParams ps{X, x_bstride, ldx, Wt, ldw, bias, bias_bstride, in_a, in_s, in_act, Y, y_bstride, ldy, y_point_major,
                     nullptr, nullptr, Cin, Cout, N};
-        pw_small_kernel<<<dim3((N + PWS_THREADS - 1) / PWS_THREADS, B), PWS_THREADS, (size_t)(Cout + 2) * Cin * sizeof(float), stream>>>(ps);
+        const size_t smem = ((size_t)(PWS_MAX_COUT + 2) * Cin + (size_t)PWS_WARPS * PWS_MAX_COUT * PWS_PTS) * sizeof(float);
+        // 32 KB of partial sums + up to 40 KB of weights: above the 48 KB default
+        SED_CUDA(cudaFuncSetAttribute(pw_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        pw_small_kernel<<<dim3((N + PWS_PTS - 1) / PWS_PTS, B), PWS_THREADS, smem, stream>>>(ps);
         SED_CHECK_LAUNCH();
         return SED_OK;
     }
