@@ -1213,7 +1213,7 @@ int knn_tc(const float* x, long long bstride, int B, int C, int N, int k, int pn
     ensure_pool_config();
     char* buf = nullptr;
     const size_t bytes_h = rows * 64 * sizeof(__half);
-    SED_CUDA(cudaMallocAsync((void**)&buf, 2 * bytes_h + (size_t)B * npad * 4 + 256, st));
+    SED_CUDA(cudaMallocAsync((void**)&buf, 2 * bytes_h + (size_t)B * npad * 4 + align_up((size_t)B * 4), st));   // + per-cloud max|x|
     __half* hi = (__half*)buf;
     __half* lo = (__half*)(buf + bytes_h);
     float* xx = (float*)(buf + 2 * bytes_h);
