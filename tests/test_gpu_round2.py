@@ -277,6 +277,24 @@ def test_two_rank_nccl_sharded_equals_single_rank(dev, tmp_path):
     assert float((gathered[:, 3:5] - single[:, 3:5]).abs().max()) < 1e-6    # mean residual, bandwidth
 
 
+def test_meanshift_pair_kernel_matches_single(dev, tmp_path):
+    """The opt-in CTA-pair kernel (cta_group::2, SEDNET_B200_MS_PAIR=1) against the default single-CTA kernel: same MMAs in
+    the same order, so results are bit-identical unless the two decompose the partial last wave differently (the
+    10 x 2100 case: 170 query tiles on 148 SMs resp. 90 pairs on 74 SM pairs, both split by key range), where partial sums
+    meet in a different order."""
+    out = tmp_path / "pair.pt"
+    env = dict(os.environ, SEDNET_B200_MS_PAIR="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ms_pair_worker.py"), str(out)], capture_output=True,
+                       text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    pair = torch.load(out)
+    from ms_pair_worker import run_cases
+    single = run_cases(dev)
+    for k, v in single.items():
+        assert torch.isfinite(pair[k]).all()
+        assert float((pair[k] - v).abs().max()) <= (1e-5 if k.startswith("B10") else 0.0), k
+
+
 # ------------------------------------------------------------------------------------------------ driver default: HPNet_embed
 def test_pipeline_clusters_the_148_column_hpnet_embedding(dev):
     """The driver's default flow (HPNet_embed = True, generate_predictions_aug.py:371-387) through the batched C-ABI step:
