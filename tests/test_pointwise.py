@@ -58,6 +58,10 @@ def _run(lib, x, W, bias, a, s, act, want_stats=False):
     (2, 1300, 128, 2, 0),           # edge head
     (1, 600, 6, 128, None),         # first EdgeConv: Cin below the tensor-core kernels
     (2, 900, 192, 64, 1),           # Cin not a multiple of 64
+    (1, 5, 64, 70, 1),              # fewer points than a lane group, Cout not a multiple of 32
+    (2, 132, 33, 96, 2),            # odd Cin (zero-padded K), ragged second tile
+    (1, 4096, 48, 200, None),       # two 128-channel groups, the second one partial
+    (3, 260, 256, 8, 2),            # widest few-output-channel layer
 ])
 def test_pointwise_matches_conv1d(lib, B, N, Cin, Cout, act):
     x, W, bias, a, s, ref = _case(B, N, Cin, Cout, act, seed=Cin + Cout)
@@ -66,14 +70,16 @@ def test_pointwise_matches_conv1d(lib, B, N, Cin, Cout, act):
     assert float((y.double() - ref).abs().max()) <= TOL * scale
 
 
-def test_pointwise_epilogue_statistics(lib):
+@pytest.mark.parametrize("N,Cin,Cout", [(1100, 256, 256), (1100, 128, 200), (333, 64, 96)])
+def test_pointwise_epilogue_statistics(lib, N, Cin, Cout):
     """stats = per (128-point tile, 32-channel block) sum and sum of squares; mm = per (tile, channel) max and min."""
-    B, N, Cin, Cout = 2, 1100, 256, 256
+    B = 2
     x, W, bias, a, s, ref = _case(B, N, Cin, Cout, 1, seed=5)
     y, stats, mm = _run(lib, x, W, bias, a, s, 1, want_stats=True)
     P = (N + 127) // 128
     pad = P * 128 - N
-    yp = F.pad(y.double(), (0, pad)).view(B, Cout // 32, 32, P, 128)
+    cpad = (Cout + 31) // 32 * 32 - Cout
+    yp = F.pad(y.double(), (0, pad, 0, cpad)).view(B, (Cout + cpad) // 32, 32, P, 128)
     s1 = yp.sum((2, 4)).permute(0, 2, 1)
     s2 = (yp * yp).sum((2, 4)).permute(0, 2, 1)
     assert torch.allclose(stats[..., 0], s1, rtol=1e-5, atol=1e-3)
