@@ -867,13 +867,12 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
     const bool pair = pair_env && has_lo;
     int width = kNumSMs;
     if (pair) {
-        static int max_clusters[2] = {0, 0};
-        int& mc = max_clusters[prec_mode == 1 ? 1 : 0];
-        if (mc == 0) {
-            TcParams q{}; q.kernel_type = kernel_type; launch_pair(prec_mode == 1 ? 2 : 1, nullptr, q, st, &mc);
-            if (sed_debug_sync()) fprintf(stderr, "[sednet_b200] mean-shift pair kernel: %d clusters resident\n", mc);
-        }
-        width = mc;
+        int mc = 0;     // queried per call: cheap next to the iterations, and correct for every device of a process
+        TcParams q{};
+        q.kernel_type = kernel_type;
+        launch_pair(prec_mode == 1 ? 2 : 1, nullptr, q, st, &mc);
+        if (sed_debug_sync()) fprintf(stderr, "[sednet_b200] mean-shift pair kernel: %d clusters resident\n", mc);
+        width = mc > 0 ? mc : kNumSMs / 2;
     }
     const int qtc_tiles = (N + TC_M - 1) / TC_M;
     const int qtc = pair ? (qtc_tiles + 1) / 2 : qtc_tiles;        // work units per cloud
