@@ -179,6 +179,22 @@ int sed_ms_bandwidth(const float* X, int B, int N, int d, int K, float min_bw, f
  *   out (B,N,d); tmp (B,N,d) scratch (ping-pong). */
 int sed_ms_shift(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type,
                  int prec_mode, float* out, float* tmp, sed_stream_t stream);
+/* The same iterations started from positions Q0 (B,N,d) instead of from the keys themselves (Q0 NULL or == X: sed_ms_shift):
+ * one step of a longer run -- the training path calls it with iterations = 1 and keeps every state for
+ * sed_ms_shift_backward_step.  Rows of 129..192 columns take the FP32 FFMA kernel here. */
+int sed_ms_shift_from(const float* X, const float* Q0, const float* bw, int B, int N, int d, int iterations, int kernel_type,
+                      int prec_mode, float* out, float* tmp, sed_stream_t stream);
+
+/* Backward of ONE mean-shift iteration (Gaussian kernel) -- the training path: src/segment_loss.py:50-56 runs
+ * mean_shift(..., iterations = 5, nms = False) inside the triplet loss and differentiates src/mean_shift.py:45-79 with
+ * autograd.  Q (B,N,d) are the positions that entered the iteration, X (B,N,d) the keys, G (B,N,d) = dL/d(positions after the
+ * iteration), bw (B) the bandwidths (constants of the graph, as in the reference: computed under no_grad).  Writes
+ * dQ (B,N,d) = dL/dQ and ADDS the iteration's dL/dX to dX_accum (B,N,d); the caller adds the final dQ (iteration 0 starts
+ * from Q = X).  d <= 128, a multiple of 4.  P and dS are recomputed tile by tile; workspace:
+ * sed_ms_shift_backward_workspace_bytes(B, N). */
+int64_t sed_ms_shift_backward_workspace_bytes(int B, int N);
+int sed_ms_shift_backward_step(const float* Q, const float* X, const float* G, const float* bw, int B, int N, int d,
+                               float* dQ, float* dX_accum, void* workspace, sed_stream_t stream);
 
 /* src/mean_shift.py:139-179 nms: centers = shifted points (B,N,d), X (B,N,d), bw (B).
  *   labels (B,N) int64; center_ids (B,max_centers) int32 ascending, n_centers (B) int32, n_labels (B) int32

@@ -383,7 +383,7 @@ using namespace sed;
 
 namespace sed {
 int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type, int prec_mode,
-                float* out, float* tmp, cudaStream_t st);
+                float* out, float* tmp, cudaStream_t st, const float* Q0);
 }
 
 extern "C" {
@@ -400,16 +400,22 @@ int sed_normalize_transpose(const float* emb, int B, int d, int N, float* X, sed
 
 int sed_ms_shift(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type, int prec_mode,
                  float* out, float* tmp, sed_stream_t stream) {
+    return sed_ms_shift_from(X, nullptr, bw, B, N, d, iterations, kernel_type, prec_mode, out, tmp, stream);
+}
+
+int sed_ms_shift_from(const float* X, const float* Q0, const float* bw, int B, int N, int d, int iterations, int kernel_type,
+                      int prec_mode, float* out, float* tmp, sed_stream_t stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (!X || !bw || !out || !tmp || B <= 0 || N <= 0 || d <= 0 || d > MS_DMAX || (d & 3) || iterations < 0)
         return SED_ERR_ARG;
     if (kernel_type != 0 && kernel_type != 1) return SED_ERR_ARG;
+    if (Q0 == X) Q0 = nullptr;
     if (iterations == 0) {
-        SED_CUDA(cudaMemcpyAsync(out, X, (size_t)B * N * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        SED_CUDA(cudaMemcpyAsync(out, Q0 ? Q0 : X, (size_t)B * N * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
         return SED_OK;
     }
     if (prec_mode >= 1 && prec_mode <= 3) {
-        const int rc = ms_shift_tc(X, bw, B, N, d, iterations, kernel_type, prec_mode, out, tmp, st);
+        const int rc = ms_shift_tc(X, bw, B, N, d, iterations, kernel_type, prec_mode, out, tmp, st, Q0);
         if (rc != SED_ERR_UNSUPPORTED) return rc;
         prec_mode = 0;   // shape outside the tensor-core kernel's range: the FP32 FFMA kernel
     }
@@ -423,7 +429,7 @@ int sed_ms_shift(const float* X, const float* bw, int B, int N, int d, int itera
     transpose_rows_kernel<<<tg, 256, 0, st>>>(X, N, d, XT);
     ++g_sed_launches;
     // ping-pong so that the last iteration lands in `out`
-    const float* cur = X;
+    const float* cur = Q0 ? Q0 : X;
     int rc = SED_OK;
     for (int it = 0; it < iterations && rc == SED_OK; ++it) {
         float* dst = ((iterations - 1 - it) & 1) ? tmp : out;

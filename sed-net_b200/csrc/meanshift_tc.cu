@@ -848,9 +848,10 @@ int ms_shift_tc192(const float* X, const float* bw, int B, int N, int d, int ite
                    cudaStream_t st);   // meanshift_tc192.cu
 
 int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterations, int kernel_type, int prec_mode,
-                float* out, float* tmp, cudaStream_t st) {
+                float* out, float* tmp, cudaStream_t st, const float* Q0) {
     (void)tmp;
     if (d > TC_D) {
+        if (Q0) return SED_ERR_UNSUPPORTED;   // foreign start positions: only the 128-wide kernels (and the FFMA kernel)
         // 129..192 columns: the only tensor-core kernel at that width runs the 3 + 1 split.  Mode 1 asks for both legs at
         // FP32 accuracy: send it to the caller's FP32 FFMA kernel rather than silently running 3 + 1.
         if (prec_mode == 1) return SED_ERR_UNSUPPORTED;
@@ -898,6 +899,11 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
            *ql[2] = {buf + 3 * elems, buf + 5 * elems};
     split_f16_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, st>>>(X, (long long)elems, d, xh, xl);
     ++g_sed_launches;
+    if (Q0) {   // start positions other than the keys (one iteration of a longer run: the training path keeps every state):
+                // their split image sits in ping-pong buffer 1, which iteration 0 reads and iteration 1 overwrites
+        split_f16_kernel<<<(unsigned)((elems / 4 + 255) / 256), 256, 0, st>>>(Q0, (long long)elems, d, qh[1], ql[1]);
+        ++g_sed_launches;
+    }
     CUtensorMap mxh, mxl, maps[4];
     int rc = make_map_f16(&mxh, xh, B, N, TC_D);
     if (rc == SED_OK) rc = make_map_f16(&mxl, xl, B, N, TC_D);
@@ -908,8 +914,8 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
     }
     for (int it = 0; it < iterations && rc == SED_OK; ++it) {
         // iteration 0 reads Q = X; iteration it > 0 reads ping-pong buffer (it-1)&1 and writes buffer it&1
-        const __half* cqh = it == 0 ? xh : qh[(it - 1) & 1];
-        const __half* cql = it == 0 ? xl : ql[(it - 1) & 1];
+        const __half* cqh = it == 0 ? (Q0 ? qh[1] : xh) : qh[(it - 1) & 1];
+        const __half* cql = it == 0 ? (Q0 ? ql[1] : xl) : ql[(it - 1) & 1];
         TcParams p{cqh, cql, bw, it == iterations - 1 ? out128 : nullptr, qh[it & 1], has_lo ? ql[it & 1] : nullptr, N,
                    kernel_type, qtc, full, parts, tpp, part_o, part_cnt, upc * (full + rem * parts)};
         rc = pair             ? launch_pair(prec_mode == 1 ? 2 : 1, maps, p, st)

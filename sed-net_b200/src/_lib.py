@@ -35,6 +35,9 @@ SIGNATURES = {
     "sed_normalize_transpose": (I, [c_f32p, I, I, I, c_f32p, c_vp]),
     "sed_ms_bandwidth": (I, [c_f32p, I, I, I, I, F, c_f32p, c_f32p, c_vp]),
     "sed_ms_shift": (I, [c_f32p, c_f32p, I, I, I, I, I, I, c_f32p, c_f32p, c_vp]),
+    "sed_ms_shift_from": (I, [c_f32p, c_f32p, c_f32p, I, I, I, I, I, I, c_f32p, c_f32p, c_vp]),
+    "sed_ms_shift_backward_workspace_bytes": (L, [I, I]),
+    "sed_ms_shift_backward_step": (I, [c_f32p, c_f32p, c_f32p, c_f32p, I, I, I, c_f32p, c_f32p, c_vp, c_vp]),
     "sed_ms_nms_workspace_bytes": (L, [I, I]),
     "sed_ms_nms": (I, [c_f32p, c_f32p, c_f32p, I, I, I, I, c_i64p, c_i32p, c_i32p, c_i32p, c_f32p, c_vp, c_vp]),
     "sed_one_hot": (I, [c_i64p, I, I, c_f32p, c_vp]),

@@ -9,6 +9,43 @@ from . import _lib
 MAX_CENTERS = 512
 
 
+class _MeanShiftIterations(torch.autograd.Function):
+    """new_X = mean_shift_(X, b, iterations) with the backward of csrc/meanshift_bwd.cu.  The forward runs the same kernels as
+    inference, one iteration per call so that the positions entering every iteration are kept ((iterations + 1) x N x d
+    floats; the reference's autograd keeps ~6 N x N tensors per iteration).  The bandwidth is a constant, as in the reference
+    (mean_shift computes it under no_grad); a row whose weights all underflow passes no gradient."""
+
+    @staticmethod
+    def forward(ctx, X, bw, iterations, mode):
+        N, d = X.shape
+        Xc = X.detach().contiguous()
+        states = [Xc]
+        tmp = torch.empty_like(Xc)
+        for _ in range(iterations):
+            out = torch.empty_like(Xc)
+            _lib.call("sed_ms_shift_from", _lib.ptr(Xc), _lib.ptr(states[-1]), _lib.ptr(bw), 1, N, d, 1, 0, mode,
+                      _lib.ptr(out), _lib.ptr(tmp), _lib.stream())
+            states.append(out)
+        ctx.save_for_backward(bw, *states[:-1])
+        ctx.shape = (N, d)
+        return states[-1].clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        bw, *states = ctx.saved_tensors
+        N, d = ctx.shape
+        X = states[0]
+        G = grad_out.contiguous().float()
+        dX = torch.zeros_like(X)
+        ws = torch.empty(_lib.load().sed_ms_shift_backward_workspace_bytes(1, N), dtype=torch.uint8, device=X.device)
+        for Q in reversed(states):
+            dQ = torch.empty_like(X)
+            _lib.call("sed_ms_shift_backward_step", _lib.ptr(Q), _lib.ptr(X), _lib.ptr(G), _lib.ptr(bw), 1, N, d,
+                      _lib.ptr(dQ), _lib.ptr(dX), _lib.ptr(ws), _lib.stream())
+            G = dQ
+        return dX + G, None, None, None
+
+
 class MeanShift:
     def __init__(self, prec_mode=None):
         """prec_mode of sed_ms_shift (include/sednet_b200.h): 0 FP32 FFMA (reference operation order), 1 tcgen05 with FP16
@@ -48,6 +85,11 @@ class MeanShift:
         X = _lib.require_cuda(X, name="X")
         N, d = X.shape
         bw = torch.as_tensor(b, dtype=torch.float32, device=X.device).reshape(1).contiguous()
+        if torch.is_grad_enabled() and X.requires_grad and int(iterations) > 0:
+            # training (src/segment_loss.py:50-56): the reference differentiates these iterations with autograd
+            if kernel_type != "gaussian":
+                raise NotImplementedError("the backward kernels cover the gaussian kernel (the one the triplet loss uses)")
+            return _MeanShiftIterations.apply(X, bw.detach(), int(iterations), self._mode(d)), X
         out, tmp = torch.empty_like(X), torch.empty_like(X)
         kt = 0 if kernel_type == "gaussian" else 1
         _lib.call("sed_ms_shift", _lib.ptr(X), _lib.ptr(bw), 1, N, d, int(iterations), kt, self._mode(d),
