@@ -171,7 +171,10 @@ int sed_ms_bandwidth(const float* X, int B, int N, int d, int K, float min_bw, f
  *   X (B,N,d), d <= 256 a multiple of 4, bw (B) device, kernel_type 0 gaussian / 1 epanechnikov.
  *   prec_mode 0 = FP32 FFMA in the reference's operation order (any d <= 256).  Tensor-core modes (tcgen05, FP16 hi/lo
  *   split operands, FP32 accumulation; rows zero-padded to 128 or 192 columns):
- *     1 = S from 3 MMAs (Qh.Xh + Qh.Xl + Ql.Xh), O from 2 (Ph.Xh + Ph.Xl): FP32-faithful on both legs (d <= 128;
+ *     4 = S from 3 MMAs (Qh.Xh + Qh.Xl + Ql.Xh), O from 3 (Ph.Xh + Ph.Xl + Pl.Xh): every operand of both legs carries
+ *         22 significant bits -- FP32-faithful (d <= 128; for 128 < d <= 256 the call runs mode 0);
+ *     1 = S from 3 MMAs, O from 2 (Ph.Xh + Ph.Xl): scores and X at 22 bits, the weights P are single FP16 values (11 bits,
+ *         unbiased rounding: ~2e-6 per iteration and point against FP32, <= 1e-4 on BASELINE's configs; d <= 128;
  *         for 128 < d <= 256 the call runs mode 0, which is at least as accurate);
  *     3 = S from 3 MMAs, O from 1 (Ph.Xh): the exponent is FP32-faithful, the weighted mean carries one FP16 rounding of
  *         X per term (d <= 192; wider rows run mode 0);

@@ -414,7 +414,7 @@ int sed_ms_shift_from(const float* X, const float* Q0, const float* bw, int B, i
         SED_CUDA(cudaMemcpyAsync(out, Q0 ? Q0 : X, (size_t)B * N * d * sizeof(float), cudaMemcpyDeviceToDevice, st));
         return SED_OK;
     }
-    if (prec_mode >= 1 && prec_mode <= 3) {
+    if (prec_mode >= 1 && prec_mode <= 4) {
         const int rc = ms_shift_tc(X, bw, B, N, d, iterations, kernel_type, prec_mode, out, tmp, st, Q0);
         if (rc != SED_ERR_UNSUPPORTED) return rc;
         prec_mode = 0;   // shape outside the tensor-core kernel's range: the FP32 FFMA kernel

@@ -17,6 +17,9 @@
 //     prec_mode 3:  S = Qh Xh + Qh Xl + Ql Xh   (3 MMAs),   O = Ph Xh           (P is FP16 anyway: the X_l term of O
 //                   only removes an unbiased 2^-12 relative rounding of X that averages out over the cluster)
 //     prec_mode 2:  S = Qh Xh,                               O = Ph Xh           (fast)
+//     prec_mode 4:  S as in mode 1,                          O = Ph Xh + Ph Xl + Pl Xh   (3 MMAs: the weights P are split as
+//                   well -- in modes 1 / 3 they are single FP16 values, 11 bits, the one rounding left that FP32 does not
+//                   have: ~2e-6 per iteration and point, up to 1.3e-4 when a broad kernel is stopped mid-flight)
 // The scale 8 keeps hi/lo away from the bottom of the FP16 range; 64 = 8*8 is folded into the exp2 argument and
 // the factor 8 on O vanishes in the normalisation.
 #include <stdlib.h>
@@ -52,7 +55,7 @@ struct TcParams {
     int grid_ctas;
 };
 
-// NS: MMAs per S tile (1 or 3); NV: MMAs per PV tile (1 or 2)
+// NS: MMAs per S tile (1 or 3); NV: MMAs per PV tile (1, 2, or 3 = P split into hi / lo as well)
 // KT: kernel type (0 gaussian, 1 epanechnikov)
 template <int NS, int NV, int KT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -165,11 +168,12 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                 const uint32_t xs = x_addr + (j % STAGES) * STAGE_BYTES;
                 const uint32_t pa = tmem + (uint32_t)(j & 1) * 128u;
 #pragma unroll
-                for (int term = 0; term < NV; ++term) {
-                    const uint32_t xb = xs + term * TILE_BYTES;
+                for (int term = 0; term < NV; ++term) {         // Ph Xh, Ph Xl, Pl Xh
+                    const uint32_t xb = xs + (term == 1 ? TILE_BYTES : 0);
+                    const uint32_t pt = pa + (term == 2 ? 32u : 0u);
 #pragma unroll
-                    for (int ks = 0; ks < TC_NK / 16; ++ks) {   // keys [0,64) at P columns [0,32), keys [64,128) at [64,96)
-                        umma_ts(tmem_o, pa + (ks >> 2) * 64 + (ks & 3) * 8, make_desc(xb + ks * 2048, BOX_BYTES), IDESC_PV,
+                    for (int ks = 0; ks < TC_NK / 16; ++ks) {   // keys [0,64) at P columns [0,32), keys [64,128) at [64,96); P_lo 32 further
+                        umma_ts(tmem_o, pt + (ks >> 2) * 64 + (ks & 3) * 8, make_desc(xb + ks * 2048, BOX_BYTES), IDESC_PV,
                                 (j > 0 || term > 0 || ks > 0) ? 1u : 0u);
                     }
                 }
@@ -228,7 +232,7 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
             tmem_ld_wait();
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-                uint32_t pk[16];
+                uint32_t pk[16], pl[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float p0, p1;
@@ -241,8 +245,14 @@ ms_shift_tc_kernel(const __grid_constant__ CUtensorMap map_xh, const __grid_cons
                     }
                     const __half2 h = __floats2half2_rn(p0, p1);   // low half = even key, high half = odd key
                     pk[i] = *reinterpret_cast<const uint32_t*>(&h);
+                    if (NV == 3) {
+                        const float2 hf = __half22float2(h);
+                        const __half2 l = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+                        pl[i] = *reinterpret_cast<const uint32_t*>(&l);
+                    }
                 }
                 tmem_st16(sb + c * 16, pk);
+                if (NV == 3) tmem_st16(sb + 32 + c * 16, pl);     // P_lo: the other half of the 64 columns this thread read
             }
             tmem_st_wait();
             tc_fence_before();
@@ -854,18 +864,18 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
         if (Q0) return SED_ERR_UNSUPPORTED;   // foreign start positions: only the 128-wide kernels (and the FFMA kernel)
         // 129..192 columns: the only tensor-core kernel at that width runs the 3 + 1 split.  Mode 1 asks for both legs at
         // FP32 accuracy: send it to the caller's FP32 FFMA kernel rather than silently running 3 + 1.
-        if (prec_mode == 1) return SED_ERR_UNSUPPORTED;
+        if (prec_mode == 1 || prec_mode == 4) return SED_ERR_UNSUPPORTED;
         return ms_shift_tc192(X, bw, B, N, d, iterations, kernel_type, out, st);
     }
     if (d <= 0 || (d & 3)) return SED_ERR_UNSUPPORTED;
     const bool padded = d < TC_D;      // the kernel works on 128-wide rows: pad with zero columns, strip them at the end
-    const bool has_lo = (prec_mode == 1 || prec_mode == 3);
+    const bool has_lo = (prec_mode == 1 || prec_mode == 3 || prec_mode == 4);
     const size_t elems = (size_t)B * N * TC_D;
     // one CTA per SM: whole waves of query tiles, then the partial wave split by key range over the idle SMs
     // SEDNET_B200_MS_PAIR=1: the CTA-pair kernel (cta_group::2) for the split modes; work units are then PAIRS of query
     // tiles (the last pair of a cloud with an odd tile count carries a ghost tile) on as many SM pairs as the device holds
     static const bool pair_env = [] { const char* e = getenv("SEDNET_B200_MS_PAIR"); return e && !strcmp(e, "1"); }();
-    const bool pair = pair_env && has_lo;
+    const bool pair = pair_env && (prec_mode == 1 || prec_mode == 3);
     int width = kNumSMs;
     if (pair) {
         int mc = 0;     // queried per call: cheap next to the iterations, and correct for every device of a process
@@ -919,6 +929,7 @@ int ms_shift_tc(const float* X, const float* bw, int B, int N, int d, int iterat
         TcParams p{cqh, cql, bw, it == iterations - 1 ? out128 : nullptr, qh[it & 1], has_lo ? ql[it & 1] : nullptr, N,
                    kernel_type, qtc, full, parts, tpp, part_o, part_cnt, upc * (full + rem * parts)};
         rc = pair             ? launch_pair(prec_mode == 1 ? 2 : 1, maps, p, st)
+             : prec_mode == 4 ? launch_tc<3, 3>(mxh, mxl, p, B, st)
              : prec_mode == 1 ? launch_tc<3, 2>(mxh, mxl, p, B, st)
              : prec_mode == 3 ? launch_tc<3, 1>(mxh, mxl, p, B, st)
                               : launch_tc<1, 1>(mxh, mxl, p, B, st);

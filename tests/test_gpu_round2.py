@@ -61,7 +61,7 @@ def config1_case():
     return dict(pts=pts, nrm=nrm, lab=lab, pred=pred, X=X, ref=ref)
 
 
-@pytest.mark.parametrize("prec", [1, 3])
+@pytest.mark.parametrize("prec", [1, 3, 4])
 def test_config1_full_size_vs_oracle(dev, config1_case, prec):
     """configs[1] through the two-phase C-ABI pipeline at full size: run_forward (both networks, k = 64), the handle's X
     and pred_type replaced by the planted ones, run_cluster (bandwidth, 50 tensor-core iterations, nms, vote, fits,
@@ -128,7 +128,7 @@ def _ms_all_modes(X, dev, iterations, check, tol3=1e-4):
     from sednet_b200.src.mean_shift import MeanShift
     with torch.no_grad():
         onew, ocen, obw, olab = O.mean_shift(X, 10000, 0.015, iterations)
-    for prec in (0, 1, 3):
+    for prec in (0, 1, 3, 4):
         newX, center, bw, labels = MeanShift(prec_mode=prec).mean_shift(X.to(dev), 10000, 0.015, iterations)
         assert torch.isfinite(newX).all(), prec
         assert abs(float(bw) - float(obw)) <= 1e-4 * float(obw), (prec, float(bw), float(obw))
@@ -275,6 +275,31 @@ def test_two_rank_nccl_sharded_equals_single_rank(dev, tmp_path):
     assert torch.equal(gathered[:, :3], single[:, :3])                      # shape id, n_labels, n_fitted
     assert torch.equal(gathered[:, 5], single[:, 5])                        # label checksum: identical segmentation
     assert float((gathered[:, 3:5] - single[:, 3:5]).abs().max()) < 1e-6    # mean residual, bandwidth
+
+
+def test_meanshift_mode4_stays_at_fp32_level_mid_flight(dev):
+    """The case a randomised sweep (tools/sweep_parity.py, seed 24) found: 1 594 points, 7 blurred patches (sigma 0.04),
+    bandwidth 0.63, stopped after 25 iterations while two clusters are still merging -- perturbations are amplified there.
+    FP32 (oracle and the FFMA kernel) stays within 1e-6 of FP64; the single-FP16 weights of modes 1 / 3 drift to 1.3e-4 /
+    1.8e-4 (2e-5 once converged at 50 iterations); mode 4, which splits the weights as well, stays at 1e-5."""
+    from sednet_b200.src.mean_shift import MeanShift
+    seed = 24
+    rng = np.random.default_rng(seed)
+    N, npatch = int(rng.integers(600, 3200)), int(rng.integers(3, 17))
+    sigma, iters = float(rng.choice([0.005, 0.01, 0.02, 0.04])), int(rng.choice([10, 25, 50]))
+    assert (N, npatch, sigma, iters) == (1594, 7, 0.04, 25)
+    _, _, lab, _, _ = synth.make_cloud(9000 + seed, N, n_patches=npatch, min_pts=30)
+    X = t(synth.make_embedding(lab, 128, sigma, 100 + seed))
+    with torch.no_grad():
+        bw = torch.clamp(O.ms_bandwidth(X, 10000, 0.015), min=0.003)
+        truth = O.ms_shift(X.double(), bw.double(), iters)
+        assert float((O.ms_shift(X, bw, iters).double() - truth).abs().max()) < 2e-6
+    err = {}
+    for prec in (0, 1, 3, 4):
+        out, _ = MeanShift(prec_mode=prec).mean_shift_(X.to(dev), b=bw, iterations=iters)
+        err[prec] = float((out.cpu().double() - truth).abs().max())
+    assert err[0] < 2e-6 and err[4] < 2e-5 and err[1] < 2e-4 and err[3] < 3e-4, err
+    assert err[4] < 0.2 * err[1], err
 
 
 def test_meanshift_pair_kernel_matches_single(dev, tmp_path):
