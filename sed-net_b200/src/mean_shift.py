@@ -52,7 +52,7 @@ class MeanShift:
         operand of both legs split into FP16 hi/lo (3 + 3 MMAs: FP32-faithful), 1 the same with single-FP16 weights (3 + 2 MMAs:
         ~2e-6 per iteration against FP32), 3 the same exponent but a single FP16 pass for the weighted mean (3 + 1 MMAs: faster;
         one FP16 rounding of X per term), 2 plain FP16.
-        None = $SEDNET_B200_MS_PREC if set, otherwise the FP32-faithful choice for the row width: mode 1 up to 128
+        None = $SEDNET_B200_MS_PREC if set, otherwise the split-operand choice for the row width: mode 1 up to 128
         columns; mode 3 for 129..192 columns (the only tensor-core kernel at that width: the 148-column hpnet embedding,
         parity-tested against the oracle in tests/test_gpu_hpnet.py); mode 0 beyond.  Mode 3 is opt-in for 128 columns."""
         import os

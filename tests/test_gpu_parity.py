@@ -495,7 +495,7 @@ def test_pipeline_guard_loop_with_planted_embeddings(dev):
 
 
 def test_meanshift_default_mode_and_narrow_embedding(dev):
-    """MeanShift() picks the FP32-faithful tensor-core mode (1: both legs split; 3 is opt-in at 128 columns and the only
+    """MeanShift() picks the split-operand tensor-core mode (1: scores and keys at 22 bits; 3 is opt-in at 128 columns and the only
     tensor-core kernel for 129..192); a narrower embedding (d = 64) runs on the same kernel zero-padded to 128 columns:
     both reproduce the oracle's partition, bandwidth and shifted points."""
     from sednet_b200.src.mean_shift import MeanShift

@@ -1,5 +1,5 @@
 """GPU parity tests added in round 2: BASELINE.json configs[1] at FULL size (10 000 points x 50 iterations) against the
-oracle in the FP32-faithful mode 1 and in the 3 + 1 split mode 3, adversarial mean-shift inputs, the guard loop up to large
+oracle in the split-operand modes 1 (headline), 3 (3 + 1) and 4 (weights split as well), adversarial mean-shift inputs, the guard loop up to large
 quantiles, and configs[4]'s sharded == unsharded property over two NCCL ranks."""
 import os
 import socket
@@ -161,7 +161,7 @@ def test_meanshift_isolated_outlier_rows(dev):
     underflows to zero) must stay finite, stay where they are and become singleton clusters, as in the oracle.
     This is also where the 3 + 1 split (mode 3) shows its limit: a singleton's weighted mean is its own row read through
     ONE FP16 rounding (O = P_h X_h), so it lands on normalize(X_h), up to 2^-12 |x| per component (1.0e-4 measured) off the
-    FP32 value -- within 2e-4, not within the 1e-4 the FP32-faithful modes 0 and 1 keep."""
+    FP32 value -- within 2e-4, not within the 1e-4 modes 0, 1 and 4 keep."""
     n = 2400
     _, _, lab, _, _ = synth.make_cloud(33, n, n_patches=5, min_pts=300)
     X = synth.make_embedding(lab, 128, 0.01, 5)
@@ -181,7 +181,7 @@ def test_meanshift_isolated_outlier_rows(dev):
 
 
 def test_meanshift_mode1_rejected_or_exact_for_wide_rows(dev):
-    """129..192 columns: mode 3 runs the 192-wide tensor-core kernel, mode 1 (both legs FP32-faithful) must not silently run
+    """129..192 columns: mode 3 runs the 192-wide tensor-core kernel, mode 1 (X split on the PV leg) must not silently run
     3 + 1 -- it takes the FP32 FFMA kernel and therefore equals mode 0 bit for bit."""
     from sednet_b200.src import _lib
     n, d = 1500, 148
