@@ -13,15 +13,18 @@
 //     rows A :  per 64-row block, over all keys:     S, P, O += P X           -> |O|, Q', dO
 //     rows B :  per 64-row block, over all keys:     S, P, dP, dS, dQ += dS X
 //     cols   :  per 64-key block, over all rows:     S^T, P^T, dP^T, dS^T, dX += P^T dO + dS^T Q
-// i.e. 9 N^2 d multiply-adds per iteration.  Tiles are 64 x 128 floats in shared memory (row pitch 132), a thread owns a 4 x 4
-// patch of the 64 x 64 score tile (rows ty + 16 r, columns tx + 16 q: conflict-free 16-byte reads) and a 4 x 8 patch of the
-// 64 x 128 accumulators.  b (the bandwidth) is a constant of the graph, as in the reference (computed under no_grad).
+// i.e. 9 N^2 d multiply-adds per iteration.  Tiles are rows x 128 floats in shared memory (row pitch 132): a CTA keeps a block
+// of 16 R rows (keys) resident and streams 64-row tiles of the other side; a thread owns an R x 4 patch of the score tile (rows
+// ty + 16 r, columns tx + 16 q: conflict-free 16-byte reads) and an R x 8 patch of the accumulators.  R is chosen per call so
+// that the CTAs fill whole waves of the 148 SMs (N = 10 000: R = 5, 125 CTAs, one wave; 64-row blocks would be 157 = two).  b (the bandwidth) is a constant of the graph, as in the reference (computed under no_grad).
+#include <type_traits>
+
 #include "common.cuh"
 #include "internal.h"
 
 namespace sed {
 
-constexpr int MB_T = 64;                 // rows / keys per tile
+constexpr int MB_T = 64;                 // rows / keys per STREAMED tile; a CTA's resident block has 16 R rows, R = 2 ... 8
 constexpr int MB_D = 128;                // channels (narrower rows are zero-padded by the loader)
 constexpr int MB_P = MB_D + 4;           // row pitch of a 64 x 128 tile
 constexpr int MB_WP = MB_T + 4;          // row pitch of a 64 x 64 weight tile
@@ -40,9 +43,9 @@ struct MsbParams {
     int N, d;
 };
 
-// rows [row0, row0 + 64) of a (N, d) matrix -> tile[64][132]; rows >= N and columns >= d read as zero
-__device__ __forceinline__ void msb_load(float* tile, const float* __restrict__ src, int row0, int N, int d) {
-    for (int e = threadIdx.x; e < MB_T * (MB_D / 4); e += MB_THREADS) {
+// rows [row0, row0 + rows) of a (N, d) matrix -> tile[rows][132]; rows >= N and columns >= d read as zero
+__device__ __forceinline__ void msb_load(float* tile, const float* __restrict__ src, int row0, int N, int d, int rows = MB_T) {
+    for (int e = threadIdx.x; e < rows * (MB_D / 4); e += MB_THREADS) {
         const int r = e >> 5, c = (e & 31) * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row0 + r < N && c < d) v = __ldg(reinterpret_cast<const float4*>(src + (long long)(row0 + r) * d + c));
@@ -50,21 +53,22 @@ __device__ __forceinline__ void msb_load(float* tile, const float* __restrict__ 
     }
 }
 
-// acc[r][q] = A[ty + 16 r] . Bm[tx + 16 q]   over the 128 channels
-__device__ __forceinline__ void msb_dot(const float* __restrict__ A, const float* __restrict__ Bm, int ty, int tx, float (&acc)[4][4]) {
+// acc[r][q] = A[ty + 16 r] . Bm[tx + 16 q]   over the 128 channels (RA rows of A per thread, 4 of Bm)
+template <int RA>
+__device__ __forceinline__ void msb_dot(const float* __restrict__ A, const float* __restrict__ Bm, int ty, int tx, float (&acc)[RA][4]) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < RA; ++r)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[r][q] = 0.f;
-#pragma unroll 4
+#pragma unroll 2
     for (int c = 0; c < MB_D; c += 4) {
-        float4 a[4], b[4];
+        float4 a[RA], b[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) a[r] = *reinterpret_cast<const float4*>(A + (ty + 16 * r) * MB_P + c);
+        for (int r = 0; r < RA; ++r) a[r] = *reinterpret_cast<const float4*>(A + (ty + 16 * r) * MB_P + c);
 #pragma unroll
         for (int q = 0; q < 4; ++q) b[q] = *reinterpret_cast<const float4*>(Bm + (tx + 16 * q) * MB_P + c);
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < RA; ++r)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 acc[r][q] = fmaf(a[r].x, b[q].x, acc[r][q]);
@@ -76,18 +80,19 @@ __device__ __forceinline__ void msb_dot(const float* __restrict__ A, const float
 }
 
 // acc[r][0..3] += sum_j W[ty + 16 r][j] T[j][4 tx ..],  acc[r][4..7] += ... T[j][64 + 4 tx ..]
-__device__ __forceinline__ void msb_update(const float* __restrict__ W, const float* __restrict__ T, int ty, int tx, float (&acc)[4][8]) {
+template <int RA>
+__device__ __forceinline__ void msb_update(const float* __restrict__ W, const float* __restrict__ T, int ty, int tx, float (&acc)[RA][8]) {
 #pragma unroll 2
     for (int j = 0; j < MB_T; j += 4) {
-        float4 w[4];
+        float4 w[RA];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) w[r] = *reinterpret_cast<const float4*>(W + (ty + 16 * r) * MB_WP + j);
+        for (int r = 0; r < RA; ++r) w[r] = *reinterpret_cast<const float4*>(W + (ty + 16 * r) * MB_WP + j);
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const float4 t0 = *reinterpret_cast<const float4*>(T + (j + jj) * MB_P + 4 * tx);
             const float4 t1 = *reinterpret_cast<const float4*>(T + (j + jj) * MB_P + 64 + 4 * tx);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < RA; ++r) {
                 const float wv = jj == 0 ? w[r].x : jj == 1 ? w[r].y : jj == 2 ? w[r].z : w[r].w;
                 acc[r][0] = fmaf(wv, t0.x, acc[r][0]); acc[r][1] = fmaf(wv, t0.y, acc[r][1]);
                 acc[r][2] = fmaf(wv, t0.z, acc[r][2]); acc[r][3] = fmaf(wv, t0.w, acc[r][3]);
@@ -106,30 +111,32 @@ __device__ __forceinline__ float msb_weight(float s, float inv_b2, bool& live) {
 }
 
 // ---------------------------------------------------------------------------------------------- rows, pass A
+template <int R>
 __global__ void __launch_bounds__(MB_THREADS) msb_rows_a_kernel(MsbParams p) {
+    constexpr int BT = 16 * R;            // rows of this CTA
     extern __shared__ __align__(16) float sm[];
-    float* Qs = sm;                       // [64][132]
-    float* Xs = Qs + MB_TILE;             // [64][132]
-    float* Ps = Xs + MB_TILE;             // [64][68]
-    float* red = Ps + MB_WTILE;           // [64][16]
-    const int b = blockIdx.y, row0 = blockIdx.x * MB_T;
+    float* Qs = sm;                       // [BT][132]
+    float* Xs = Qs + BT * MB_P;           // [64][132]
+    float* Ps = Xs + MB_TILE;             // [BT][68]
+    float* red = Ps + BT * MB_WP;         // [BT][16]
+    const int b = blockIdx.y, row0 = blockIdx.x * BT;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     const long long off = (long long)b * p.N * p.d;
     const float bwv = p.bw[b], inv_b2 = 1.0f / (bwv * bwv);
-    msb_load(Qs, p.Q + off, row0, p.N, p.d);
-    float O[4][8];
+    msb_load(Qs, p.Q + off, row0, p.N, p.d, BT);
+    float O[R][8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c) O[r][c] = 0.f;
     for (int k0 = 0; k0 < p.N; k0 += MB_T) {
         __syncthreads();                                      // previous tile's readers are done (and Qs is loaded)
         msb_load(Xs, p.X + off, k0, p.N, p.d);
         __syncthreads();
-        float s[4][4];
+        float s[R][4];
         msb_dot(Qs, Xs, ty, tx, s);
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 bool live;
@@ -140,9 +147,9 @@ __global__ void __launch_bounds__(MB_THREADS) msb_rows_a_kernel(MsbParams p) {
         msb_update(Ps, Xs, ty, tx, O);
     }
     // |O| and Q' . G per row: sums over the 16 threads that share a row
-    float g[4][8];
+    float g[R][8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < R; ++r) {
         const int row = row0 + ty + 16 * r;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -154,16 +161,16 @@ __global__ void __launch_bounds__(MB_THREADS) msb_rows_a_kernel(MsbParams p) {
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < R; ++r) {
         float ss = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) ss = fmaf(O[r][c], O[r][c], ss);
         red[(ty + 16 * r) * 16 + tx] = ss;
     }
     __syncthreads();
-    float rn[4];
+    float rn[R];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < R; ++r) {
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) ss += red[(ty + 16 * r) * 16 + i];
@@ -171,7 +178,7 @@ __global__ void __launch_bounds__(MB_THREADS) msb_rows_a_kernel(MsbParams p) {
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < R; ++r) {
         float dt = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; ++c) dt = fmaf(O[r][c] * rn[r], g[r][c], dt);
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(MB_THREADS) msb_rows_a_kernel(MsbParams p) {
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < R; ++r) {
         float dt = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) dt += red[(ty + 16 * r) * 16 + i];
@@ -200,32 +207,34 @@ __global__ void __launch_bounds__(MB_THREADS) msb_rows_a_kernel(MsbParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------- rows, pass B
+template <int R>
 __global__ void __launch_bounds__(MB_THREADS) msb_rows_b_kernel(MsbParams p) {
+    constexpr int BT = 16 * R;
     extern __shared__ __align__(16) float sm[];
-    float* Qs = sm;
-    float* Ds = Qs + MB_TILE;             // dO rows of this block
-    float* Xs = Ds + MB_TILE;
-    float* Ws = Xs + MB_TILE;             // dS tile [64][68]
-    const int b = blockIdx.y, row0 = blockIdx.x * MB_T;
+    float* Qs = sm;                       // [BT][132]
+    float* Ds = Qs + BT * MB_P;           // dO rows of this block
+    float* Xs = Ds + BT * MB_P;           // [64][132]
+    float* Ws = Xs + MB_TILE;             // dS tile [BT][68]
+    const int b = blockIdx.y, row0 = blockIdx.x * BT;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     const long long off = (long long)b * p.N * p.d;
     const float bwv = p.bw[b], inv_b2 = 1.0f / (bwv * bwv);
-    msb_load(Qs, p.Q + off, row0, p.N, p.d);
-    msb_load(Ds, p.dO + (long long)b * p.N * MB_D, row0, p.N, MB_D);
-    float dQ[4][8];
+    msb_load(Qs, p.Q + off, row0, p.N, p.d, BT);
+    msb_load(Ds, p.dO + (long long)b * p.N * MB_D, row0, p.N, MB_D, BT);
+    float dQ[R][8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c) dQ[r][c] = 0.f;
     for (int k0 = 0; k0 < p.N; k0 += MB_T) {
         __syncthreads();
         msb_load(Xs, p.X + off, k0, p.N, p.d);
         __syncthreads();
-        float s[4][4], dp[4][4];
+        float s[R][4], dp[R][4];
         msb_dot(Qs, Xs, ty, tx, s);
         msb_dot(Ds, Xs, ty, tx, dp);
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 bool live;
@@ -236,7 +245,7 @@ __global__ void __launch_bounds__(MB_THREADS) msb_rows_b_kernel(MsbParams p) {
         msb_update(Ws, Xs, ty, tx, dQ);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < R; ++r) {
         const int row = row0 + ty + 16 * r;
         if (row >= p.N) continue;
 #pragma unroll
@@ -250,21 +259,23 @@ __global__ void __launch_bounds__(MB_THREADS) msb_rows_b_kernel(MsbParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------- columns (keys)
+template <int R>
 __global__ void __launch_bounds__(MB_THREADS) msb_cols_kernel(MsbParams p) {
+    constexpr int BT = 16 * R;            // keys of this CTA
     extern __shared__ __align__(16) float sm[];
-    float* Xs = sm;                       // this block's keys
-    float* Qs = Xs + MB_TILE;             // streamed rows
+    float* Xs = sm;                       // this block's keys [BT][132]
+    float* Qs = Xs + BT * MB_P;           // streamed rows [64][132]
     float* Ds = Qs + MB_TILE;             // their dO
-    float* Pt = Ds + MB_TILE;             // P^T  [key][row]
-    float* St = Pt + MB_WTILE;            // dS^T [key][row]
-    const int b = blockIdx.y, key0 = blockIdx.x * MB_T;
+    float* Pt = Ds + MB_TILE;             // P^T  [key][row]  [BT][68]
+    float* St = Pt + BT * MB_WP;          // dS^T [key][row]
+    const int b = blockIdx.y, key0 = blockIdx.x * BT;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
     const long long off = (long long)b * p.N * p.d;
     const float bwv = p.bw[b], inv_b2 = 1.0f / (bwv * bwv);
-    msb_load(Xs, p.X + off, key0, p.N, p.d);
-    float dX[4][8];
+    msb_load(Xs, p.X + off, key0, p.N, p.d, BT);
+    float dX[R][8];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < R; ++r)
 #pragma unroll
         for (int c = 0; c < 8; ++c) dX[r][c] = 0.f;
     for (int r0 = 0; r0 < p.N; r0 += MB_T) {
@@ -272,11 +283,11 @@ __global__ void __launch_bounds__(MB_THREADS) msb_cols_kernel(MsbParams p) {
         msb_load(Qs, p.Q + off, r0, p.N, p.d);
         msb_load(Ds, p.dO + (long long)b * p.N * MB_D, r0, p.N, MB_D);
         __syncthreads();
-        float s[4][4], dp[4][4];
+        float s[R][4], dp[R][4];
         msb_dot(Xs, Qs, ty, tx, s);                          // s[r][q] = X[key ty + 16 r] . Q[row tx + 16 q]
         msb_dot(Xs, Ds, ty, tx, dp);
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
+        for (int r = 0; r < R; ++r)
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 bool live;
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(MB_THREADS) msb_cols_kernel(MsbParams p) {
         msb_update(St, Qs, ty, tx, dX);
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < R; ++r) {
         const int key = key0 + ty + 16 * r;
         if (key >= p.N) continue;
 #pragma unroll
@@ -320,20 +331,44 @@ int sed_ms_shift_backward_step(const float* Q, const float* X, const float* G, c
     if (!Q || !X || !G || !bw || !dQ || !dX_accum || !workspace || B <= 0 || N <= 0 || d <= 0) return SED_ERR_ARG;
     if (d > MB_D || (d & 3)) return SED_ERR_UNSUPPORTED;
     MsbParams p{Q, X, G, bw, (float*)workspace, dQ, dX_accum, N, d};
-    const dim3 grid((N + MB_T - 1) / MB_T, B);
-    const size_t sm_a = (size_t)(2 * MB_TILE + MB_WTILE + MB_T * 16) * sizeof(float);
-    const size_t sm_b = (size_t)(3 * MB_TILE + MB_WTILE) * sizeof(float);
-    const size_t sm_c = (size_t)(3 * MB_TILE + 2 * MB_WTILE) * sizeof(float);
-    SED_CUDA(cudaFuncSetAttribute(msb_rows_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));
-    SED_CUDA(cudaFuncSetAttribute(msb_rows_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
-    SED_CUDA(cudaFuncSetAttribute(msb_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-    msb_rows_a_kernel<<<grid, MB_THREADS, sm_a, st>>>(p);
-    SED_CHECK_LAUNCH();
-    msb_rows_b_kernel<<<grid, MB_THREADS, sm_b, st>>>(p);
-    SED_CHECK_LAUNCH();
-    msb_cols_kernel<<<grid, MB_THREADS, sm_c, st>>>(p);
-    SED_CHECK_LAUNCH();
-    return SED_OK;
+    // rows (keys) per CTA = 16 R: the R that needs the fewest CTA-rows of work in whole waves (one CTA per SM).  At
+    // N = 10 000 the natural 64 gives 157 CTAs = two waves on 148 SMs, 80 gives 125 = one.
+    int best = 4;
+    long long best_cost = -1;
+    for (int R : {2, 3, 4, 5, 6, 8}) {
+        const long long ctas = (long long)((N + 16 * R - 1) / (16 * R)) * B;
+        const long long cost = ((ctas + kNumSMs - 1) / kNumSMs) * R;
+        if (best_cost < 0 || cost < best_cost) { best = R; best_cost = cost; }
+    }
+    int rc = SED_OK;
+    auto go = [&](auto tag) -> int {
+        constexpr int R = decltype(tag)::value;
+        constexpr int BT = 16 * R;
+        const dim3 grid((N + BT - 1) / BT, B);
+        const size_t sm_a = (size_t)(BT * MB_P + MB_TILE + BT * MB_WP + BT * 16) * sizeof(float);
+        const size_t sm_b = (size_t)(2 * BT * MB_P + MB_TILE + BT * MB_WP) * sizeof(float);
+        const size_t sm_c = (size_t)(BT * MB_P + 2 * MB_TILE + 2 * BT * MB_WP) * sizeof(float);
+        static_assert((size_t)(8 * 16 * MB_P + 2 * MB_TILE + 2 * 8 * 16 * MB_WP) * sizeof(float) <= 227 * 1024, "shared memory budget");
+        SED_CUDA(cudaFuncSetAttribute(msb_rows_a_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a));
+        SED_CUDA(cudaFuncSetAttribute(msb_rows_b_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b));
+        SED_CUDA(cudaFuncSetAttribute(msb_cols_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        msb_rows_a_kernel<R><<<grid, MB_THREADS, sm_a, st>>>(p);
+        SED_CHECK_LAUNCH();
+        msb_rows_b_kernel<R><<<grid, MB_THREADS, sm_b, st>>>(p);
+        SED_CHECK_LAUNCH();
+        msb_cols_kernel<R><<<grid, MB_THREADS, sm_c, st>>>(p);
+        SED_CHECK_LAUNCH();
+        return SED_OK;
+    };
+    switch (best) {
+        case 2: rc = go(std::integral_constant<int, 2>{}); break;
+        case 3: rc = go(std::integral_constant<int, 3>{}); break;
+        case 5: rc = go(std::integral_constant<int, 5>{}); break;
+        case 6: rc = go(std::integral_constant<int, 6>{}); break;
+        case 8: rc = go(std::integral_constant<int, 8>{}); break;
+        default: rc = go(std::integral_constant<int, 4>{}); break;
+    }
+    return rc;
 }
 
 }  // extern "C"
