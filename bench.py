@@ -7,10 +7,10 @@ One "step" = one pass of the hot path over one batch of 8 synthetic 10 000-point
 configs[1]): two SEDNet forwards (type net, instance net), type argmax, normalise, guarded mean-shift (50 iterations),
 per-segment type vote, primitive fits, residuals.  Prints ONE JSON line on rank 0.
 
-The headline `value` / `e2e` are measured with mean-shift mode 1 (scores and keys as FP16 hi/lo splits = 22 bits, the exp
-weights as single FP16 values, FP32 accumulation: labels identical and shifted points within 1e-4 of the FP32 oracle on
-BASELINE's configs); the faster 3 + 1 split mode 3 and the strict mode 4 (weights split as well: within 1e-5 of FP64
-everywhere) are measured in the same invocation and reported under `modes` (DESIGN.md section 5 has the measured deviations).  Further legs (rank 0, N = 1 unless stated): the clustering half on planted embeddings (`planted`), BASELINE's
+The headline `value` / `e2e` are measured with mean-shift mode 4 (every operand of both GEMM legs -- positions, keys and the
+exp weights -- as FP16 hi/lo splits = 22 bits, FP32 accumulation: within 1e-5 of an FP64 evaluation everywhere, the level of
+FP32 itself); the faster modes 1 (single-FP16 weights, 5 MMAs instead of 6) and 3 (additionally no X_lo term in the weighted
+mean, 4 MMAs) are measured in the same invocation and reported under `modes` (DESIGN.md section 5 has the measured deviations).  Further legs (rank 0, N = 1 unless stated): the clustering half on planted embeddings (`planted`), BASELINE's
 configs[2] / [3] (`configs`), 64 clouds per GPU with one all-gather of the per-shape records at the end (`config4`, every
 N), the kNN kernel alone (`roofline.kernels`), the reference's eager PyTorch code on the same GPU (`gpu_eager_baseline`)
 and on the host cores (`cpu_baseline`).
@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 METRIC, UNIT = "point_clouds_per_sec_10k_seg_fit", "clouds/s"
 BATCH, NPTS, KNN, ITERS, QUANTILE, DIM = 8, 10000, 64, 50, 0.015, 128
 WORKLOAD = "configs[1]: batch=8 x 10000-pt clouds, 2x SEDNet forward (k=64) + mean-shift(50 it) + type vote + fits"
-HEADLINE_MODE, FAST_MODE, STRICT_MODE = 1, 3, 4
+HEADLINE_MODE, MID_MODE, FAST_MODE = 4, 1, 3        # headline: every operand of both legs at 22 bits
 DTYPES = {0: "f32", 1: "f16-split(3+2),f32-acc", 2: "f16,f32-acc", 3: "f16-split(3+1),f32-acc", 4: "f16-split(3+3),f32-acc"}
 MMA_PER_PAIR = {0: 0, 1: 5, 2: 2, 3: 4, 4: 6}
 KERNEL = {0: "ms_shift_ffma_kernel", 1: "ms_shift_tc_kernel<3,2> (FP16 hi/lo split: S 3 MMAs, PV 2)",
@@ -291,7 +291,7 @@ def kernel_legs(dev, pk):
     ws = torch.empty(lib.sed_ms_nms_workspace_bytes(B, NPTS), dtype=torch.uint8, device=dev)
     res = torch.empty((B, S), device=dev)
     row = {}
-    for mode in (HEADLINE_MODE, FAST_MODE):
+    for mode in (HEADLINE_MODE, MID_MODE, FAST_MODE):
         def chain():
             _lib.call("sed_ms_bandwidth", _lib.ptr(X), B, NPTS, DIM, 150, 0.003, _lib.ptr(kth), _lib.ptr(bw), _lib.stream())
             _lib.call("sed_ms_shift", _lib.ptr(X), _lib.ptr(bw), B, NPTS, DIM, ITERS, 0, mode, _lib.ptr(out), _lib.ptr(tmp),
@@ -404,8 +404,8 @@ def run_ours(args, rank, world, local_rank):
                 "executed_tflops": achieved * MMA_PER_PAIR[mode] / 2.0, "share_of_step": stage["shift"] / (ms_dev / args.steps)}
 
     head = measure(HEADLINE_MODE, True)
+    mid = measure(MID_MODE, False)
     fast = measure(FAST_MODE, False)
-    strict = measure(STRICT_MODE, False)
 
     # ---- 64 clouds per GPU (configs[4] when N = 8): 8 batches through the handle, records kept on the device, ONE
     # all-gather at the end; the gathered table is checked against the rank-local records
@@ -437,7 +437,7 @@ def run_ours(args, rank, world, local_rank):
             Xp[b] = torch.from_numpy(synth.make_embedding(lab[b], DIM, 0.02, 300 + b))
         Xp, tp = Xp.to(dev), torch.from_numpy(typ[:BATCH].astype(np.int32)).to(dev)
         planted = {}
-        for mode in (HEADLINE_MODE, FAST_MODE):
+        for mode in (HEADLINE_MODE, MID_MODE, FAST_MODE):
             for _ in range(3):
                 pipe.run_forward(P_dev, N_dev)
                 view("X").copy_(Xp); view("pred_type").copy_(tp)
@@ -462,34 +462,30 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         h2d = 2 * BATCH * NPTS * 3 * 4
         tf_peak = pk["tf"]
-        # DRAM bytes of one launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum, `ncu --set full`
-        # at this shape, B = 8): profiles/ms_shift_tc_r2.md (mode 1), profiles/ms_shift_tc_r1c.md (mode 3)
-        traffic = {3: 82.010368e6 + 16.861440e6}.get(HEADLINE_MODE)
+        # DRAM bytes of one launch of the kernels (dram__bytes_read.sum + dram__bytes_write.sum, `ncu --set full` at this
+        # shape, B = 8): profiles/ms_shift_traffic_r2.json (profiles/ms_shift_tc_r2c.md mode 4, ms_shift_tc_r2b.md mode 1,
+        # ms_shift_tc_r1c.md mode 3)
+        traffic = {3: 82.010368e6 + 16.861440e6}
         tfile = os.path.join(ROOT, "profiles", "ms_shift_traffic_r2.json")
         if os.path.exists(tfile):
             with open(tfile) as f:
-                traffic = json.load(f).get(str(HEADLINE_MODE), traffic)
-        ms_roof = {"kernel": KERNEL[HEADLINE_MODE], "bound": "tensor", "achieved": head["achieved_tflops"], "peak": tf_peak,
-                   "unit": "TFLOP/s", "frac": head["achieved_tflops"] / tf_peak, "traffic": traffic,
-                   "traffic_unit": "bytes per launch (ncu --set full, profiles/)",
-                   "algorithmic_bytes_per_launch": BATCH * 3.0 * NPTS * DIM * 4,
-                   "peak_source": pk["how"] + " dense bf16 sustained (fp16 and bf16 share the tcgen05 rate)",
-                   "executed_tflops": head["executed_tflops"], "executed_frac": head["executed_tflops"] / tf_peak,
-                   "executed_frac_of_burst": (head["executed_tflops"] / pk["tf_burst"]) if pk.get("tf_burst") else None,
-                   "note": "achieved = algorithmic FLOP (2 GEMMs of 2*N*N*d per cloud and iteration) / measured launch time "
-                           "(CUDA events the library records around the shift stage on the run's stream / iterations); the "
-                           "FP16 hi/lo split executes mma_per_pair/2 times that on the tensor pipe (executed_*)",
-                   "mma_per_gemm_pair": MMA_PER_PAIR[HEADLINE_MODE], "share_of_step": head["share_of_step"]}
+                traffic.update({int(k): v for k, v in json.load(f).items() if k.isdigit()})
+
+        def roof_of(m):
+            return {"kernel": KERNEL[m["mode"]], "bound": "tensor", "achieved": m["achieved_tflops"], "peak": tf_peak,
+                    "unit": "TFLOP/s", "frac": m["achieved_tflops"] / tf_peak, "traffic": traffic.get(m["mode"]),
+                    "traffic_unit": "bytes per launch (ncu --set full, profiles/)",
+                    "algorithmic_bytes_per_launch": float(BATCH * 3 * NPTS * DIM * 4),
+                    "executed_tflops": m["executed_tflops"], "executed_frac": m["executed_tflops"] / tf_peak,
+                    "executed_frac_of_burst": (m["executed_tflops"] / pk["tf_burst"]) if pk.get("tf_burst") else None,
+                    "mma_per_gemm_pair": MMA_PER_PAIR[m["mode"]], "share_of_step": m["share_of_step"]}
+        ms_roof = roof_of(head)
+        ms_roof["peak_source"] = pk["how"] + " dense bf16 sustained (fp16 and bf16 share the tcgen05 rate)"
+        ms_roof["note"] = ("achieved = algorithmic FLOP (2 GEMMs of 2*N*N*d per cloud and iteration) / measured launch time (CUDA "
+                           "events the library records around the shift stage on the run's stream / iterations); the FP16 hi/lo "
+                           "split executes mma_per_gemm_pair/2 times that on the tensor pipe (executed_*)")
         roof = dict(ms_roof)
-        roof["kernels"] = [ms_roof,
-                           {"kernel": KERNEL[FAST_MODE], "bound": "tensor", "achieved": fast["achieved_tflops"], "peak": tf_peak,
-                            "unit": "TFLOP/s", "frac": fast["achieved_tflops"] / tf_peak, "traffic": 82.010368e6 + 16.861440e6,
-                            "executed_tflops": fast["executed_tflops"], "executed_frac": fast["executed_tflops"] / tf_peak,
-                            "share_of_step": fast["share_of_step"]},
-                           {"kernel": KERNEL[STRICT_MODE], "bound": "tensor", "achieved": strict["achieved_tflops"], "peak": tf_peak,
-                            "unit": "TFLOP/s", "frac": strict["achieved_tflops"] / tf_peak, "traffic": None,
-                            "executed_tflops": strict["executed_tflops"], "executed_frac": strict["executed_tflops"] / tf_peak,
-                            "share_of_step": strict["share_of_step"]}] + kernels
+        roof["kernels"] = [ms_roof, roof_of(mid), roof_of(fast)] + kernels
         mode_view = lambda m: {k: m[k] for k in ("mode", "dtype", "value", "e2e", "ms_per_step", "e2e_ms_per_step", "stage_ms",
                                                   "guard_retries", "gpu_launches", "gather_checked")}
         line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -505,14 +501,14 @@ def run_ours(args, rank, world, local_rank):
                         "ms_per_step": head["e2e_ms_per_step"]},
                 "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "roofline": roof,
                 "stage_ms": head["stage_ms"],
-                "modes": {"headline": f"mode {HEADLINE_MODE}: scores S = Q.X^T and the keys X as FP16 hi/lo splits (22 bits), the "
-                                      "weights P = exp(.) as single FP16 values, FP32 accumulation: labels identical and "
-                                      "shifted points <= 1e-4 of the FP32 oracle on BASELINE's configs (tests); "
-                                      f"mode {STRICT_MODE} splits P as well (every operand 22 bits: ~1e-6 of FP64, the "
-                                      "level of FP32 itself), mode 3 drops the X_lo term of the weighted mean; "
-                                      "measured deviations: DESIGN.md section 5",
-                          str(HEADLINE_MODE): mode_view(head), str(FAST_MODE): mode_view(fast),
-                          str(STRICT_MODE): mode_view(strict)},
+                "modes": {"headline": f"mode {HEADLINE_MODE}: every operand of both mean-shift GEMM legs (Q, X and the exp weights P) "
+                                      "as FP16 hi/lo splits = 22 bits, FP32 accumulation: within 1e-5 of an FP64 evaluation "
+                                      "everywhere, the level of FP32 itself; partitions identical to the FP32 oracle's wherever "
+                                      f"the FP32 FFMA path's are.  mode {MID_MODE} keeps P as single FP16 values (5 MMAs), mode "
+                                      f"{FAST_MODE} also drops the X_lo term of the weighted mean (4 MMAs): identical labels on "
+                                      "BASELINE's configs, up to 3e-4 / 5e-4 off and a flipped point on heavily overlapping "
+                                      "clusters (DESIGN.md section 5)",
+                          str(HEADLINE_MODE): mode_view(head), str(MID_MODE): mode_view(mid), str(FAST_MODE): mode_view(fast)},
                 "config4": c4}
         if planted is not None:
             line["planted"] = planted

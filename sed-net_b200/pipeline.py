@@ -56,7 +56,7 @@ class Pipeline:
         i, k2 = _host_table(sd_inst)
         _lib.call("sed_pipeline_set_weights", self._h, t, i)
 
-    def run_host(self, points, normals, quantile=0.015, iterations=50, prec_mode=1):
+    def run_host(self, points, normals, quantile=0.015, iterations=50, prec_mode=4):
         """points, normals: (B,N,3) float32 HOST tensors (pinned for full copy speed). Returns dict of host tensors
         (views into pinned result buffers, valid until the next call)."""
         B = points.shape[0]
@@ -70,7 +70,7 @@ class Pipeline:
                   _lib.ptr(o["bw"]), _lib.ptr(o["n_labels"]), _lib.stream())
         return {k: v[:B] for k, v in o.items()}
 
-    def run_device(self, points, normals, quantile=0.015, iterations=50, prec_mode=1):
+    def run_device(self, points, normals, quantile=0.015, iterations=50, prec_mode=4):
         """points, normals: (B,N,3) float32 CUDA tensors; results stay on the device (see ``device_tensor``)."""
         points = _lib.require_cuda(points, name="points")
         normals = _lib.require_cuda(normals, name="normals")
@@ -102,10 +102,10 @@ class Pipeline:
 
     def run_cluster(self, points, normals, quantile=0.015, iterations=50, prec_mode=None):
         """Second half: guarded mean-shift of the handle's X, type vote, fits, residuals (results on the device).
-        prec_mode None = 1 for rows up to 128 wide, 3 for wider ones (the tensor-core kernel of 129..192 columns; mode 1
+        prec_mode None = 4 for rows up to 128 wide, 3 for wider ones (the tensor-core kernel of 129..192 columns; modes 1 and 4
         would take the FP32 FFMA kernel there, ~30x slower)."""
         if prec_mode is None:
-            prec_mode = 1 if getattr(self, "_d", 128) <= 128 else 3
+            prec_mode = 4 if getattr(self, "_d", 128) <= 128 else 3
         points = _lib.require_cuda(points, name="points")
         normals = _lib.require_cuda(normals, name="normals")
         B = points.shape[0]

@@ -52,8 +52,10 @@ class MeanShift:
         operand of both legs split into FP16 hi/lo (3 + 3 MMAs: FP32-faithful), 1 the same with single-FP16 weights (3 + 2 MMAs:
         ~2e-6 per iteration against FP32), 3 the same exponent but a single FP16 pass for the weighted mean (3 + 1 MMAs: faster;
         one FP16 rounding of X per term), 2 plain FP16.
-        None = $SEDNET_B200_MS_PREC if set, otherwise the split-operand choice for the row width: mode 1 up to 128
-        columns; mode 3 for 129..192 columns (the only tensor-core kernel at that width: the 148-column hpnet embedding,
+        None = $SEDNET_B200_MS_PREC if set, otherwise the most faithful tensor-core mode for the row width: mode 4 up to 128
+        columns (partitions identical to the FP32 oracle's wherever the FP32 FFMA kernel's are; modes 1 and 3 are opt-in: faster,
+        identical labels on separated clusters, up to 5e-4 off and a flipped point on heavily overlapping ones); mode 3 for
+        129..192 columns (the only tensor-core kernel at that width: the 148-column hpnet embedding,
         parity-tested against the oracle in tests/test_gpu_hpnet.py); mode 0 beyond.  Mode 3 is opt-in for 128 columns."""
         import os
         env = os.environ.get("SEDNET_B200_MS_PREC")
@@ -63,7 +65,7 @@ class MeanShift:
         if self.prec_mode is not None:
             return self.prec_mode
         if d % 4 == 0 and d <= 128:
-            return 1
+            return 4
         return 3 if d % 4 == 0 and d <= 192 else 0
 
     # -- src/mean_shift.py:19-43

@@ -69,7 +69,7 @@ def test_forward_is_deterministic(dev, clouds):
     assert _same(enc)
 
 
-@pytest.mark.parametrize("mode", [1, 3])
+@pytest.mark.parametrize("mode", [4, 1, 3])
 def test_meanshift_is_deterministic(dev, clouds, mode):
     """Bandwidth, 50 iterations and nms on 8 clouds of planted embeddings, four times."""
     from sednet_b200.src.mean_shift import MeanShift
@@ -87,7 +87,7 @@ def test_meanshift_is_deterministic(dev, clouds, mode):
 
 
 def test_pipeline_step_is_deterministic(dev, clouds):
-    """The whole batched step (2 forwards + clustering + vote + fits) through the pipeline handle, mode 1."""
+    """The whole batched step (2 forwards + clustering + vote + fits) through the pipeline handle, default mode (4)."""
     from sednet_b200.pipeline import Pipeline
     x6, _ = clouds
     B = 8
@@ -98,7 +98,7 @@ def test_pipeline_step_is_deterministic(dev, clouds):
     pipe.set_weights(sd1, sd2)
     outs = []
     for _ in range(4):
-        pipe.run_device(pts, nrm, prec_mode=1)
+        pipe.run_device(pts, nrm)
         torch.cuda.synchronize()
         outs.append(tuple(pipe.device_tensor(name)[:B].clone() for name in ("X", "labels", "pred_type", "params", "residual", "bw")))
     assert _same(outs)

@@ -495,15 +495,15 @@ def test_pipeline_guard_loop_with_planted_embeddings(dev):
 
 
 def test_meanshift_default_mode_and_narrow_embedding(dev):
-    """MeanShift() picks the split-operand tensor-core mode (1: scores and keys at 22 bits; 3 is opt-in at 128 columns and the only
-    tensor-core kernel for 129..192); a narrower embedding (d = 64) runs on the same kernel zero-padded to 128 columns:
+    """MeanShift() picks the most faithful tensor-core mode (4: every operand of both legs at 22 bits; 1 and 3 are opt-in at 128
+    columns, 3 is the only tensor-core kernel for 129..192); a narrower embedding (d = 64) runs on the same kernel zero-padded to 128 columns:
     both reproduce the oracle's partition, bandwidth and shifted points."""
     from sednet_b200.src.mean_shift import MeanShift
     _, _, lab, _, _ = synth.make_cloud(91, 2500, n_patches=7, min_pts=250)
     for d in (128, 64):
         X = t(synth.make_embedding(lab, d, 0.02, 17))
         ms = MeanShift()
-        assert ms._mode(d) == 1 and MeanShift()._mode(148) == 3 and MeanShift()._mode(50) == 0 and MeanShift()._mode(200) == 0
+        assert ms._mode(d) == 4 and MeanShift()._mode(148) == 3 and MeanShift()._mode(50) == 0 and MeanShift()._mode(200) == 0
         newX, center, bw, labels = ms.mean_shift(X.to(dev), 10000, 0.015, 20)
         with torch.no_grad():
             rX, rc, rbw, rlab = O.mean_shift(X, 10000, 0.015, 20)

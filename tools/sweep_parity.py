@@ -14,15 +14,18 @@ from util import canon, comparable_params, cylinder_fp64, rel_err, sign_align
 
 s0 = int(sys.argv[1]) if len(sys.argv) > 1 else 0
 ns = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+only = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else None
 dev = torch.device("cuda")
 torch.set_num_threads(os.cpu_count())
 bad = 0
-for seed in range(s0, s0 + ns):
+for seed in (only or range(s0, s0 + ns)):
     rng = np.random.default_rng(seed)
     N = int(rng.integers(600, 3200))
     npatch = int(rng.integers(3, 17))
     sigma = float(rng.choice([0.005, 0.01, 0.02, 0.04]))
     iters = int(rng.choice([10, 25, 50]))
+    if os.environ.get("SWEEP_ITERS"):
+        iters = int(os.environ["SWEEP_ITERS"])      # e.g. 50: the driver's setting for every cloud
     pts, nrm, lab, typ, _ = synth.make_cloud(9000 + seed, N, n_patches=npatch, min_pts=30)
     X = torch.from_numpy(synth.make_embedding(lab, 128, sigma, 100 + seed))
     with torch.no_grad():
@@ -37,7 +40,15 @@ for seed in range(s0, s0 + ns):
         err = float((newX.cpu() - onew).abs().max())
         bwe = abs(float(bw) - float(obw)) / float(obw)
         if not same or err > {0: 5e-5, 1: 1e-4, 3: 2e-4, 4: 5e-5}[prec] or bwe > 1e-4:
-            msg.append(f"mode {prec}: partition {'same' if same else 'DIFFERENT'} shifted {err:.2e} bw {bwe:.1e}")
+            detail = ""
+            if not same:    # how different: segment counts and the share of points that agree under the best one-to-one matching
+                from scipy.optimize import linear_sum_assignment
+                a, b_ = canon(l), canon(ol)
+                C = np.zeros((a.max() + 1, b_.max() + 1), np.int64)
+                np.add.at(C, (a, b_), 1)
+                ri, ci = linear_sum_assignment(-C)
+                detail = f" ({a.max() + 1} vs {b_.max() + 1} segments, {C[ri, ci].sum() / len(a):.4f} of the points agree)"
+            msg.append(f"mode {prec}: partition {'same' if same else 'DIFFERENT' + detail} shifted {err:.2e} bw {bwe:.1e}")
     # fits on the oracle's segments: vote + fit through the product's dispatcher vs the oracle's
     n_seg = int(ol.max()) + 1
     st = O.segment_types(typ, ol, n_seg)
