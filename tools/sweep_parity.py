@@ -24,6 +24,8 @@ for seed in (only or range(s0, s0 + ns)):
     npatch = int(rng.integers(3, 17))
     sigma = float(rng.choice([0.005, 0.01, 0.02, 0.04]))
     iters = int(rng.choice([10, 25, 50]))
+    if os.environ.get("SWEEP_N"):
+        N = int(os.environ["SWEEP_N"])              # e.g. 10000: BASELINE's cloud size (the oracle then takes ~40 s per cloud)
     if os.environ.get("SWEEP_ITERS"):
         iters = int(os.environ["SWEEP_ITERS"])      # e.g. 50: the driver's setting for every cloud
     pts, nrm, lab, typ, _ = synth.make_cloud(9000 + seed, N, n_patches=npatch, min_pts=30)
