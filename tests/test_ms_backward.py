@@ -36,7 +36,7 @@ def dev():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 4])
 def test_gradient_matches_reference_fixture(dev, golden, mode):
     """Relative to the largest gradient entry: 2e-4 (the forward states come from the FP32 FFMA kernel resp. the FP16-split
     tensor-core kernel, the backward recomputes the weights in FP32 with ex2.approx)."""
