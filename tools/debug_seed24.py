@@ -1,3 +1,6 @@
+"""Deviation of every mean-shift precision mode from an FP64 evaluation of the same iterations, as a function of the iteration
+count, on one cloud of the randomised sweep (default: seed 24, the worst case of tools/sweep_parity.py) -- the numbers of the
+table in DESIGN.md section 5.   python tools/debug_seed24.py [seed]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
