@@ -143,7 +143,7 @@ def test_meanshift_vs_oracle(dev, n, npatch, sigma, kernel):
         onew, ocen, obw, olab = O.mean_shift(X, 10000, 0.015, 20, kernel)
     newX, center, bw, labels = MeanShift(prec_mode=0).mean_shift(X.to(dev), 10000, 0.015, 20, kernel_type=kernel)
     assert abs(float(bw) - float(obw)) < 1e-4 * float(obw)
-    assert float((newX.cpu() - onew).abs().max()) < (2e-5 if prec == 4 else 1e-4)
+    assert float((newX.cpu() - onew).abs().max()) < 2e-5
     assert (canon(labels.cpu().numpy()) == canon(olab.numpy())).all()
     assert float((torch.linalg.norm(newX, dim=1) - 1).abs().max()) < 1e-5         # stays on the unit sphere
 
