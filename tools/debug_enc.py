@@ -1,4 +1,5 @@
-"""Debug: encoder forward at a given batch size (python tools/debug_enc.py B [N])."""
+"""Debug: encoder + full forward at a given batch size, optionally repeated with a bit-equality check
+(python tools/debug_enc.py B [N] [reps])."""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -20,3 +21,11 @@ print("encode ok", float(x4.abs().max()), float(feats.abs().max()))
 out = m(x)
 torch.cuda.synchronize()
 print("forward ok", float(out[0].abs().max()))
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # repeat and require identical bits (synchronisation bugs show as differences)
+first = [o.clone() for o in (out[0], out[1], out[3])]
+for r in range(reps):
+    o = m(x)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(first, (o[0], o[1], o[3]))), f"rep {r}: outputs differ"
+if reps:
+    print(f"{reps} repetitions bit-identical")
