@@ -64,6 +64,26 @@ inline void ensure_pool_config() {
 
 inline int64_t align_up(int64_t v, int64_t a = 256) { return (v + a - 1) / a * a; }
 
+// Prepared 1x1-convolution weights (FP16 hi / lo split, per-row power-of-two scale) of a caller whose FP32 weights do not
+// change between explicit invalidations -- the pipeline handle (sed_pipeline_set_weights).  While a cache is bound to the
+// calling thread, the tensor-core pointwise GEMMs look weight matrices that lie inside one of its registered address ranges up
+// by (pointer, pitch, shape, padding) and split them ONCE instead of on every call (round 1 re-split ~24 matrices per
+// network and step).  Anything outside the ranges -- workspace buffers such as the folded EdgeConv weights, whose pointer is
+// reused for different contents -- takes the stream-ordered temporary path.
+struct PwCache;
+PwCache* pw_cache_create();
+void pw_cache_destroy(PwCache* c);
+void pw_cache_clear(PwCache* c);                                      // the weights changed: drop every prepared matrix
+void pw_cache_add_range(PwCache* c, const void* lo, size_t bytes);    // an address range of immutable weights
+void pw_cache_bind(PwCache* c);                                       // thread-local; nullptr switches the cache off
+struct PwCacheScope {                                                 // binds for a scope (early returns included)
+    explicit PwCacheScope(PwCache* c) { pw_cache_bind(c); }
+    ~PwCacheScope() { pw_cache_bind(nullptr); }
+};
+// device buffer [Wh | Wl | rscale] (Cout x pad halves, twice, then Cout floats; parts aligned to 256 B) of W (Cout, Cin) with
+// row pitch ldw: from the bound cache, or a temporary of stream `st` that the caller releases with cudaFreeAsync
+int pw_prepared(const float* W, int ldw, int Cout, int Cin, int pad, cudaStream_t st, char** buf, bool* temporary);
+
 // bump allocator over a caller-provided workspace
 struct Arena {
     char* base; int64_t off, cap;

@@ -65,6 +65,7 @@ struct sed_pipeline {
     float* wbuf[2];
     const float* wptr[2][SED_P_COUNT];
     bool have_weights;
+    PwCache* pw_cache;              // FP16 hi / lo images of the 1x1-convolution weights, split once per set_weights
     // device buffers
     float *pts, *nrm, *inp, *emb, *logp, *edges, *emb2, *logp2, *edges2, *X, *shifted, *tmp, *kth, *bw, *centers, *params,
         *residual;
@@ -119,6 +120,7 @@ void sed_pipeline_destroy(sed_pipeline_t* p) {
     if (p->ev_fork) cudaEventDestroy(p->ev_fork);
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     if (p->side) cudaStreamDestroy(p->side);
+    if (p->pw_cache) pw_cache_destroy(p->pw_cache);
     delete p;
 }
 
@@ -157,6 +159,9 @@ int sed_pipeline_create(int max_B, int N, int k, int max_segments, sed_pipeline_
     if (rc == SED_OK && cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = SED_ERR_CUDA_BASE - 2;
     if (rc == SED_OK && cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming) != cudaSuccess) rc = SED_ERR_CUDA_BASE - 2;
     if (rc != SED_OK) { sed_pipeline_destroy(p); return rc; }
+    p->pw_cache = pw_cache_create();
+    pw_cache_add_range(p->pw_cache, p->wbuf[0], (size_t)wtot);
+    pw_cache_add_range(p->pw_cache, p->wbuf[1], (size_t)wtot);
     *out = p;
     return SED_OK;
 }
@@ -175,6 +180,7 @@ int sed_pipeline_set_weights(sed_pipeline_t* p, const float* const* type_params_
             off += align_up(bytes);
         }
     }
+    pw_cache_clear(p->pw_cache);   // the prepared images belong to the previous weights
     p->have_weights = true;
     return SED_OK;
 }
@@ -207,6 +213,7 @@ int sed_pipeline_run_forward(sed_pipeline_t* p, const float* points_dev, const f
     cudaStream_t st = (cudaStream_t)stream;
     if (!p || !points_dev || !normals_dev || B <= 0 || B > p->max_B || !p->have_weights) return SED_ERR_ARG;
     const int N = p->N, S = p->S;
+    PwCacheScope weights_prepared_once(p->pw_cache);
     SED_CUDA(cudaEventRecord(p->ev[0], st));
     pack_input_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(points_dev, normals_dev, N, p->inp);
     SED_CHECK_LAUNCH();

@@ -13,6 +13,9 @@
 //   * D += Ah.Bh + Ah.Bl + Al.Bh : 22 significant bits per operand, FP32 accumulation;
 //   * epilogue: thread = point (TMEM lane), 32 output channels at a time: bias, statistics (sum / sum of squares per
 //     32-channel block, FP64 partials), max / min over the tile's points (recursive-halving shuffles), coalesced stores.
+#include <utility>
+#include <vector>
+
 #include "tc_common.cuh"
 
 namespace sed {
@@ -332,6 +335,66 @@ __global__ void pw_prep_weights_kernel(const float* __restrict__ W, int ldw, int
     if (lane == 0) rscale[row] = 1.0f / sc;
 }
 
+struct PwCacheEntry {
+    const float* W; int ldw, Cout, Cin, pad;
+    char* buf; cudaStream_t st; cudaEvent_t ready;
+};
+struct PwCache {
+    std::vector<PwCacheEntry> entries;
+    std::vector<std::pair<const char*, size_t>> ranges;
+};
+static thread_local PwCache* t_pw_cache = nullptr;
+
+PwCache* pw_cache_create() { return new PwCache(); }
+void pw_cache_clear(PwCache* c) {
+    if (!c) return;
+    for (auto& e : c->entries) { cudaFree(e.buf); cudaEventDestroy(e.ready); }    // cudaFree synchronises: no use is in flight
+    c->entries.clear();
+}
+void pw_cache_destroy(PwCache* c) { pw_cache_clear(c); delete c; }
+void pw_cache_add_range(PwCache* c, const void* lo, size_t bytes) { if (c) c->ranges.emplace_back((const char*)lo, bytes); }
+void pw_cache_bind(PwCache* c) { t_pw_cache = c; }
+
+int pw_prep_weights(const float* W, int ldw, int Cout, int Cin, int cin_pad, __half* Wh, __half* Wl, float* rscale,
+                    cudaStream_t st);
+
+int pw_prepared(const float* W, int ldw, int Cout, int Cin, int pad, cudaStream_t st, char** buf, bool* temporary) {
+    const size_t wbytes = (size_t)Cout * pad * sizeof(__half);
+    const size_t bytes = 2 * align_up(wbytes) + (size_t)Cout * sizeof(float);
+    PwCache* c = t_pw_cache;
+    bool in_range = false;
+    if (c)
+        for (auto& r : c->ranges) in_range |= ((const char*)W >= r.first && (const char*)W < r.first + r.second);
+    if (in_range) {
+        for (auto& e : c->entries)
+            if (e.W == W && e.ldw == ldw && e.Cout == Cout && e.Cin == Cin && e.pad == pad) {
+                if (e.st != st) SED_CUDA(cudaStreamWaitEvent(st, e.ready, 0));    // prepared on another stream
+                *buf = e.buf; *temporary = false;
+                return SED_OK;
+            }
+        PwCacheEntry e{W, ldw, Cout, Cin, pad, nullptr, st, nullptr};
+        SED_CUDA(cudaMalloc((void**)&e.buf, bytes));
+        const int rc = pw_prep_weights(W, ldw, Cout, Cin, pad, (__half*)e.buf, (__half*)(e.buf + align_up(wbytes)),
+                                       (float*)(e.buf + 2 * align_up(wbytes)), st);
+        if (rc != SED_OK || cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventRecord(e.ready, st) != cudaSuccess) {
+            cudaFree(e.buf);
+            return rc != SED_OK ? rc : SED_ERR_CUDA_BASE - 1;
+        }
+        c->entries.push_back(e);
+        *buf = e.buf; *temporary = false;
+        return SED_OK;
+    }
+    ensure_pool_config();
+    char* b = nullptr;
+    SED_CUDA(cudaMallocAsync((void**)&b, bytes, st));
+    const int rc = pw_prep_weights(W, ldw, Cout, Cin, pad, (__half*)b, (__half*)(b + align_up(wbytes)),
+                                   (float*)(b + 2 * align_up(wbytes)), st);
+    if (rc != SED_OK) { cudaFreeAsync(b, st); return rc; }
+    *buf = b; *temporary = true;
+    return SED_OK;
+}
+
 int pw_prep_weights(const float* W, int ldw, int Cout, int Cin, int cin_pad, __half* Wh, __half* Wl, float* rscale,
                     cudaStream_t st) {
     pw_prep_weights_kernel<<<(Cout + 7) / 8, 256, 0, st>>>(W, ldw, Cout, Cin, cin_pad, Wh, Wl, rscale);
@@ -360,14 +423,12 @@ int pw_gemm_tc(const float* X, long long x_bstride, int ldx, const float* Wt, in
     if (Cin < 32 || Cin > 4096 || Cout <= 0) return SED_ERR_UNSUPPORTED;
     const int cin_pad = (Cin + PT_KC - 1) / PT_KC * PT_KC;
     const size_t wbytes = (size_t)Cout * cin_pad * sizeof(__half);
-    ensure_pool_config();
     char* buf = nullptr;
-    SED_CUDA(cudaMallocAsync((void**)&buf, 2 * align_up(wbytes) + (size_t)Cout * sizeof(float), st));
+    bool temporary = true;
+    SED_TRY(pw_prepared(Wt, ldw, Cout, Cin, cin_pad, st, &buf, &temporary));
     __half* Wh = (__half*)buf;
     __half* Wl = (__half*)(buf + align_up(wbytes));
     float* rscale = (float*)(buf + 2 * align_up(wbytes));
-    pw_prep_weights_kernel<<<(Cout + 7) / 8, 256, 0, st>>>(Wt, ldw, Cout, Cin, cin_pad, Wh, Wl, rscale);
-    ++g_sed_launches;
     CUtensorMap mh, ml;
     int rc = make_map_w(&mh, Wh, Cout, cin_pad);
     if (rc == SED_OK) rc = make_map_w(&ml, Wl, Cout, cin_pad);
@@ -386,7 +447,7 @@ int pw_gemm_tc(const float* X, long long x_bstride, int ldx, const float* Wt, in
             if (e != cudaSuccess) rc = SED_ERR_CUDA_BASE - (int)e;
         }
     }
-    cudaFreeAsync(buf, st);
+    if (temporary) cudaFreeAsync(buf, st);
     return rc;
 }
 

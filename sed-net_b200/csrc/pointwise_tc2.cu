@@ -422,13 +422,13 @@ int pw_gemm_tc2(const float* X, long long x_bstride, int ldx, const float* Wt, i
     if ((ldx & 3) || (x_bstride & 3) || (reinterpret_cast<uintptr_t>(X) & 15)) return SED_ERR_UNSUPPORTED;
     const int kpad = (Cin + P2_KC - 1) / P2_KC * P2_KC;
     const size_t wbytes = (size_t)Cout * kpad * sizeof(__half);
-    ensure_pool_config();
     char* buf = nullptr;
-    SED_CUDA(cudaMallocAsync((void**)&buf, 2 * align_up(wbytes) + (size_t)Cout * sizeof(float), st));
+    bool temporary = true;
+    SED_TRY(pw_prepared(Wt, ldw, Cout, Cin, kpad, st, &buf, &temporary));    // split once per matrix when a cache is bound
     __half* Wh = (__half*)buf;
     __half* Wl = (__half*)(buf + align_up(wbytes));
     float* rscale = (float*)(buf + 2 * align_up(wbytes));
-    int rc = pw_prep_weights(Wt, ldw, Cout, Cin, kpad, Wh, Wl, rscale, st);
+    int rc = SED_OK;
     const int tiles_per_cloud = (N + P2_N - 1) / P2_N;
     const int groups = (Cout + P2_M - 1) / P2_M;
     const int G = std::max(1, std::min(kNumSMs / groups, B * tiles_per_cloud));
@@ -456,7 +456,7 @@ int pw_gemm_tc2(const float* X, long long x_bstride, int ldx, const float* Wt, i
         e = cudaGetLastError();
         if (e != cudaSuccess) rc = SED_ERR_CUDA_BASE - (int)e;
     }
-    cudaFreeAsync(buf, st);
+    if (temporary) cudaFreeAsync(buf, st);
     return rc;
 }
 

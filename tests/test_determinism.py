@@ -102,3 +102,31 @@ def test_pipeline_step_is_deterministic(dev, clouds):
         torch.cuda.synchronize()
         outs.append(tuple(pipe.device_tensor(name)[:B].clone() for name in ("X", "labels", "pred_type", "params", "residual", "bw")))
     assert _same(outs)
+
+
+def test_pipeline_weights_can_be_replaced(dev, clouds):
+    """The handle keeps FP16 hi / lo images of its 1x1-convolution weights across steps (split once per set_weights): a second
+    set_weights must drop them -- the outputs then equal those of a fresh handle built with the new weights, bit for bit."""
+    from sednet_b200.pipeline import Pipeline
+    x6, _ = clouds
+    B = 4
+    pts = x6[:B, :3].permute(0, 2, 1).contiguous()
+    nrm = x6[:B, 3:].permute(0, 2, 1).contiguous()
+    sd = [synth.make_state_dict(s, randomize_gn=True) for s in (1, 2, 3, 4)]
+
+    def outputs(pipe):
+        pipe.run_forward(pts, nrm)
+        torch.cuda.synchronize()
+        return tuple(pipe.device_tensor(name)[:B].clone() for name in ("X", "log_prob", "type_log_prob"))
+
+    pipe = Pipeline(B, N, k=64)
+    pipe.set_weights(sd[0], sd[1])
+    first = outputs(pipe)
+    assert _same([first, outputs(pipe)])                 # second step: prepared weights reused
+    pipe.set_weights(sd[2], sd[3])
+    second = outputs(pipe)
+    assert not torch.equal(first[0], second[0])
+    fresh = Pipeline(B, N, k=64)
+    fresh.set_weights(sd[2], sd[3])
+    assert _same([second, outputs(fresh)])
+    pipe.close(); fresh.close()
